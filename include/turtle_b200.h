@@ -1,0 +1,210 @@
+/*
+ * turtle_b200.h -- batched, GPU-resident entry points added on top of turtle.h.
+ *
+ * The scalar interface (turtle.h) describes a geometry with turtle_stepper_add_*
+ * and steps ONE particle per call (ref: src/turtle/stepper.c:780-875). The entry
+ * points below freeze such a geometry into a device-resident plan (DEM tiles in
+ * HBM, flattened layer/meta/data/transform tables) and run the same stepping
+ * rules for millions of independent rays per call on one B200. There is no CPU
+ * fallback: without a CUDA device every function here returns
+ * TURTLE_RETURN_LIBRARY_ERROR and raises through the error handler.
+ *
+ * Conventions
+ *  - plain C ABI: pointers + sizes only. `*_batch` takes HOST pointers (staged
+ *    through pinned buffers, chunked and overlapped with compute); `*_batch_device`
+ *    takes DEVICE pointers valid on the plan's device plus a `cudaStream_t`
+ *    passed as `void *` (NULL = legacy default stream) and is asynchronous.
+ *  - arrays are AoS like the scalar API: position[n][3], direction[n][3],
+ *    elevation[n][2], index[n][2].
+ *  - per-element conditions (outside of every map, NaN input ...) are reported in
+ *    per-element outputs, never through the error handler. The handler is used
+ *    for argument / launch errors only, with the reference's message format
+ *    (ref: src/turtle/error.c:108-138).
+ */
+#ifndef TURTLE_B200_H
+#define TURTLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "turtle.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* A geometry frozen on one device. Built from a turtle_stepper, it captures the
+ * layers, the geoid and the range / slope / resolution settings at freeze time
+ * (ref: the state walked by stepper_sample, src/turtle/stepper.c:703-756). */
+struct turtle_plan;
+
+/* Per-particle stepping state kept on the device between turtle_stepper_step_batch
+ * calls: what `struct turtle_stepper` keeps for ONE particle in the reference
+ * (last sample + local-approximation references, ref: src/turtle/stepper.h:45-58,
+ * 93-110). */
+struct turtle_states;
+
+/* Number of media with their own path-length accumulator in a trace result;
+ * steps started in medium >= TURTLE_TRACE_MEDIA-1 share the last one. */
+#define TURTLE_TRACE_MEDIA 4
+
+/* Why a traced ray stopped. */
+enum turtle_trace_status {
+        TURTLE_TRACE_ALTITUDE = 0, /* altitude left ]altitude_min, altitude_max[ */
+        TURTLE_TRACE_DOMAIN = 1,   /* index[0] < 0: no data below/above any more */
+        TURTLE_TRACE_LENGTH = 2,   /* travelled >= length_max */
+        TURTLE_TRACE_STEPS = 3,    /* did max_steps steps */
+        TURTLE_TRACE_INVALID = 4   /* non finite input */
+};
+
+/* Stop rule of the canonical ray loop (ref: examples/example-stepper.c:128-140:
+ * `while (altitude < altitude_max) turtle_stepper_step(...)`), made total. A ray
+ * keeps stepping while index[0] >= 0, altitude_min < altitude < altitude_max,
+ * length < length_max and n_steps < max_steps. */
+struct turtle_trace_rule {
+        double altitude_min;
+        double altitude_max;
+        double length_max;
+        int32_t max_steps;
+        int32_t reserved;
+};
+
+/* Result record of one ray (96 bytes). `length[m]` sums the steps that STARTED in
+ * medium m, i.e. `if (initial_layer == m) length += step`
+ * (ref: examples/example-stepper.c:136-139). */
+struct turtle_trace_result {
+        double position[3]; /* final ECEF position */
+        double altitude;    /* final altitude (geoid corrected if a geoid is set) */
+        double length[TURTLE_TRACE_MEDIA];
+        double total;       /* sum of all step lengths, in stepping order */
+        int32_t n_steps;    /* number of turtle_stepper_step equivalents */
+        int32_t status;     /* enum turtle_trace_status */
+        int32_t index[2];   /* final layer / data index */
+        uint32_t medium_hash; /* order dependent hash of the media visited */
+        int32_t n_changes;  /* number of steps that ended in another medium */
+};
+
+/* Kernel counters of the last trace/step call on a plan. */
+struct turtle_plan_counters {
+        uint64_t rays;     /* rays or particles processed */
+        uint64_t steps;    /* turtle_stepper_step equivalents */
+        uint64_t samples;  /* geometry samples (stepper_sample equivalents) */
+        uint64_t launches; /* CUDA kernels launched */
+        double kernel_ms;  /* device time of the kernels (CUDA events), host-pointer calls only */
+};
+
+/* ---- plans ---------------------------------------------------------------- */
+
+/* Upload every map / tile referenced by `stepper` to `device` and flatten the
+ * geometry. Stacks are made fully resident (all tiles of the grid are loaded):
+ * this replaces the reference's on-demand tile cache (ref: src/turtle/stack.c:
+ * 399-450, src/turtle/client.c:99-188). The stepper and its maps must outlive
+ * nothing: the plan owns device copies. */
+TURTLE_API enum turtle_return turtle_stepper_freeze(
+    struct turtle_stepper * stepper, int device, struct turtle_plan ** plan);
+TURTLE_API void turtle_plan_destroy(struct turtle_plan ** plan);
+TURTLE_API int turtle_plan_device(const struct turtle_plan * plan);
+/* Bytes of HBM held by the plan (tiles + tables). */
+TURTLE_API size_t turtle_plan_bytes(const struct turtle_plan * plan);
+TURTLE_API void turtle_plan_counters_get(
+    const struct turtle_plan * plan, struct turtle_plan_counters * counters);
+/* After a `*_device` call and once the caller has synchronised its stream: read
+ * the step / sample counters of that launch back from the device. */
+TURTLE_API void turtle_plan_counters_sync(struct turtle_plan * plan);
+/* Tuning: CTAs per SM and threads per CTA of the persistent kernels (0 = default). */
+TURTLE_API void turtle_plan_launch_set(
+    struct turtle_plan * plan, int ctas_per_sm, int threads);
+
+/* ---- whole rays: reset, query, then step until the rule stops the ray ------ */
+TURTLE_API enum turtle_return turtle_stepper_trace_batch(
+    struct turtle_plan * plan, size_t n, const double * position,
+    const double * direction, const struct turtle_trace_rule * rule,
+    struct turtle_trace_result * results);
+TURTLE_API enum turtle_return turtle_stepper_trace_batch_device(
+    struct turtle_plan * plan, size_t n, const double * position,
+    const double * direction, const struct turtle_trace_rule * rule,
+    struct turtle_trace_result * results, void * stream);
+
+/* ---- one turtle_stepper_step for n independent particles -------------------
+ * Same outputs as the scalar call (any output pointer may be NULL; direction
+ * NULL = query mode, position untouched). `states` may be NULL: every particle
+ * then starts from a reset stepper (exact when range <= 0). */
+TURTLE_API enum turtle_return turtle_states_create(
+    struct turtle_plan * plan, size_t n, struct turtle_states ** states);
+TURTLE_API void turtle_states_destroy(struct turtle_states ** states);
+TURTLE_API enum turtle_return turtle_states_reset(struct turtle_states * states);
+TURTLE_API enum turtle_return turtle_stepper_step_batch(
+    struct turtle_plan * plan, struct turtle_states * states, size_t n,
+    double * position, const double * direction, double * latitude,
+    double * longitude, double * altitude, double * elevation, double * step,
+    int * index);
+TURTLE_API enum turtle_return turtle_stepper_step_batch_device(
+    struct turtle_plan * plan, struct turtle_states * states, size_t n,
+    double * position, const double * direction, double * latitude,
+    double * longitude, double * altitude, double * elevation, double * step,
+    int * index, void * stream);
+
+/* ---- ray origins (ref: turtle_stepper_position, src/turtle/stepper.c:877-931)
+ * data_index[i] = -1 and position[i] untouched when (lat, lon) has no data. */
+TURTLE_API enum turtle_return turtle_stepper_position_batch(
+    struct turtle_plan * plan, size_t n, const double * latitude,
+    const double * longitude, const double * height, int layer_index,
+    double * position, int * data_index);
+
+/* ---- frame transforms (ref: src/turtle/ecef.c:41-55,63-130,160-178) ---------
+ * Run on the current CUDA device. Output pointers of to_geodetic may be NULL. */
+TURTLE_API enum turtle_return turtle_ecef_to_geodetic_batch(size_t n,
+    const double * ecef, double * latitude, double * longitude,
+    double * altitude);
+TURTLE_API enum turtle_return turtle_ecef_to_geodetic_batch_device(size_t n,
+    const double * ecef, double * latitude, double * longitude,
+    double * altitude, void * stream);
+TURTLE_API enum turtle_return turtle_ecef_from_geodetic_batch(size_t n,
+    const double * latitude, const double * longitude,
+    const double * elevation, double * ecef);
+TURTLE_API enum turtle_return turtle_ecef_from_geodetic_batch_device(size_t n,
+    const double * latitude, const double * longitude,
+    const double * elevation, double * ecef, void * stream);
+TURTLE_API enum turtle_return turtle_ecef_from_horizontal_batch(size_t n,
+    const double * latitude, const double * longitude, const double * azimuth,
+    const double * elevation, double * direction);
+TURTLE_API enum turtle_return turtle_ecef_from_horizontal_batch_device(size_t n,
+    const double * latitude, const double * longitude, const double * azimuth,
+    const double * elevation, double * direction, void * stream);
+
+/* ---- elevation queries (ref: turtle_map_elevation, src/turtle/map.c:229-277)
+ * The map is mirrored on the current device on first use and after any
+ * turtle_map_fill. z[i] is untouched where inside[i] == 0. */
+TURTLE_API enum turtle_return turtle_map_elevation_batch(
+    struct turtle_map * map, size_t n, const double * x, const double * y,
+    double * z, int * inside);
+TURTLE_API enum turtle_return turtle_map_elevation_batch_device(
+    struct turtle_map * map, size_t n, const double * x, const double * y,
+    double * z, int * inside, void * stream);
+/* Fused ECEF -> geodetic -> (projection) -> bilinear elevation: one pass over the
+ * points, no intermediate arrays in HBM. latitude/longitude/altitude may be NULL. */
+TURTLE_API enum turtle_return turtle_map_elevation_ecef_batch(
+    struct turtle_map * map, size_t n, const double * ecef, double * latitude,
+    double * longitude, double * altitude, double * z, int * inside);
+TURTLE_API enum turtle_return turtle_map_elevation_ecef_batch_device(
+    struct turtle_map * map, size_t n, const double * ecef, double * latitude,
+    double * longitude, double * altitude, double * z, int * inside,
+    void * stream);
+
+/* ---- host bulk set-up ---------------------------------------------------------*/
+/* turtle_map_fill for every node: elevation[iy * nx + ix] (ref: map.c:183-203).
+ * Stops at the first node that turtle_map_fill rejects and returns its code. */
+TURTLE_API enum turtle_return turtle_map_fill_batch(
+    struct turtle_map * map, const double * elevation);
+
+/* ---- device utilities -------------------------------------------------------*/
+/* Number of CUDA devices visible (0 when there is no driver / GPU). */
+TURTLE_API int turtle_b200_device_count(void);
+/* Measured FP64 FMA rate of the current device in Gop/s (1 FMA = 1 op), from a
+ * dependent-chain DFMA micro-benchmark kernel; used as the compute roofline. */
+TURTLE_API double turtle_b200_dfma_peak(int repeats);
+TURTLE_API const char * turtle_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

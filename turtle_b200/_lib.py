@@ -1,0 +1,154 @@
+"""ctypes binding of libturtle_b200.so (the C ABI of include/turtle.h + turtle_b200.h).
+
+The library is built in-tree by ``turtle_b200.build`` (nvcc, sm_100a). There is no
+Python or CPU fallback for the batched path: if the shared library is missing the
+import fails loudly, and the batch calls themselves fail without a CUDA device.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libturtle_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+
+
+class MapInfo(C.Structure):
+    """struct turtle_map_info (ref: include/turtle.h:93-106)."""
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("x", C.c_double * 2),
+                ("y", C.c_double * 2), ("z", C.c_double * 2),
+                ("encoding", C.c_char_p)]
+
+
+class TraceRule(C.Structure):
+    """struct turtle_trace_rule (include/turtle_b200.h)."""
+    _fields_ = [("altitude_min", C.c_double), ("altitude_max", C.c_double),
+                ("length_max", C.c_double), ("max_steps", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class PlanCounters(C.Structure):
+    """struct turtle_plan_counters (include/turtle_b200.h)."""
+    _fields_ = [("rays", C.c_uint64), ("steps", C.c_uint64),
+                ("samples", C.c_uint64), ("launches", C.c_uint64),
+                ("kernel_ms", C.c_double)]
+
+
+ERROR_HANDLER = C.CFUNCTYPE(None, C.c_int, C.c_void_p, C.c_char_p)
+
+# name -> (restype, argtypes). Every symbol declared in include/*.h is listed: the
+# CPU test-suite checks that the library exports all of them.
+_P = C.c_void_p
+_PP = C.POINTER(C.c_void_p)
+_D = C.c_double
+_I = C.c_int
+_N = C.c_size_t
+SIGNATURES = {
+    # turtle.h -- error handling
+    "turtle_error_function": (C.c_char_p, [_P]),
+    "turtle_error_handler_get": (_P, []),
+    "turtle_error_handler_set": (None, [_P]),
+    # projections
+    "turtle_projection_create": (_I, [_PP, C.c_char_p]),
+    "turtle_projection_destroy": (None, [_PP]),
+    "turtle_projection_configure": (_I, [_P, C.c_char_p]),
+    "turtle_projection_name": (C.c_char_p, [_P]),
+    "turtle_projection_project": (_I, [_P, _D, _D, c_double_p, c_double_p]),
+    "turtle_projection_unproject": (_I, [_P, _D, _D, c_double_p, c_double_p]),
+    # maps
+    "turtle_map_create": (_I, [_PP, C.POINTER(MapInfo), C.c_char_p]),
+    "turtle_map_destroy": (None, [_PP]),
+    "turtle_map_load": (_I, [_PP, C.c_char_p]),
+    "turtle_map_fill": (_I, [_P, _I, _I, _D]),
+    "turtle_map_node": (_I, [_P, _I, _I, c_double_p, c_double_p, c_double_p]),
+    "turtle_map_elevation": (_I, [_P, _D, _D, c_double_p, c_int_p]),
+    "turtle_map_projection": (_P, [_P]),
+    "turtle_map_meta": (None, [_P, C.POINTER(MapInfo), C.POINTER(C.c_char_p)]),
+    # ecef
+    "turtle_ecef_from_geodetic": (None, [_D, _D, _D, c_double_p]),
+    "turtle_ecef_to_geodetic": (None, [c_double_p, c_double_p, c_double_p, c_double_p]),
+    "turtle_ecef_from_horizontal": (None, [_D, _D, _D, _D, c_double_p]),
+    "turtle_ecef_to_horizontal": (None, [_D, _D, c_double_p, c_double_p, c_double_p]),
+    # stacks / clients
+    "turtle_stack_create": (_I, [_PP, C.c_char_p, _I, _P, _P]),
+    "turtle_stack_destroy": (None, [_PP]),
+    "turtle_stack_clear": (_I, [_P]),
+    "turtle_stack_load": (_I, [_P]),
+    "turtle_stack_elevation": (_I, [_P, _D, _D, c_double_p, c_int_p]),
+    "turtle_client_create": (_I, [_PP, _P]),
+    "turtle_client_destroy": (_I, [_PP]),
+    "turtle_client_clear": (_I, [_P]),
+    "turtle_client_elevation": (_I, [_P, _D, _D, c_double_p, c_int_p]),
+    # stepper
+    "turtle_stepper_create": (_I, [_PP]),
+    "turtle_stepper_destroy": (_I, [_PP]),
+    "turtle_stepper_geoid_set": (None, [_P, _P]),
+    "turtle_stepper_geoid_get": (_P, [_P]),
+    "turtle_stepper_reset": (None, [_P]),
+    "turtle_stepper_range_set": (None, [_P, _D]),
+    "turtle_stepper_range_get": (_D, [_P]),
+    "turtle_stepper_slope_get": (_D, [_P]),
+    "turtle_stepper_slope_set": (None, [_P, _D]),
+    "turtle_stepper_resolution_get": (_D, [_P]),
+    "turtle_stepper_resolution_set": (None, [_P, _D]),
+    "turtle_stepper_add_layer": (_I, [_P]),
+    "turtle_stepper_add_stack": (_I, [_P, _P, _D]),
+    "turtle_stepper_add_map": (_I, [_P, _P, _D]),
+    "turtle_stepper_add_flat": (_I, [_P, _D]),
+    "turtle_stepper_step": (_I, [_P, c_double_p, c_double_p, c_double_p, c_double_p,
+                                 c_double_p, c_double_p, c_double_p, c_int_p]),
+    "turtle_stepper_position": (_I, [_P, _D, _D, _D, _I, c_double_p, c_int_p]),
+    # turtle_b200.h -- plans
+    "turtle_stepper_freeze": (_I, [_P, _I, _PP]),
+    "turtle_plan_destroy": (None, [_PP]),
+    "turtle_plan_device": (_I, [_P]),
+    "turtle_plan_bytes": (_N, [_P]),
+    "turtle_plan_counters_get": (None, [_P, C.POINTER(PlanCounters)]),
+    "turtle_plan_counters_sync": (None, [_P]),
+    "turtle_plan_launch_set": (None, [_P, _I, _I]),
+    # rays
+    "turtle_stepper_trace_batch": (_I, [_P, _N, _P, _P, C.POINTER(TraceRule), _P]),
+    "turtle_stepper_trace_batch_device": (_I, [_P, _N, _P, _P, C.POINTER(TraceRule), _P, _P]),
+    # particle steps
+    "turtle_states_create": (_I, [_P, _N, _PP]),
+    "turtle_states_destroy": (None, [_PP]),
+    "turtle_states_reset": (_I, [_P]),
+    "turtle_stepper_step_batch": (_I, [_P, _P, _N] + [_P] * 8),
+    "turtle_stepper_step_batch_device": (_I, [_P, _P, _N] + [_P] * 8 + [_P]),
+    "turtle_stepper_position_batch": (_I, [_P, _N, _P, _P, _P, _I, _P, _P]),
+    # frames
+    "turtle_ecef_to_geodetic_batch": (_I, [_N, _P, _P, _P, _P]),
+    "turtle_ecef_to_geodetic_batch_device": (_I, [_N, _P, _P, _P, _P, _P]),
+    "turtle_ecef_from_geodetic_batch": (_I, [_N, _P, _P, _P, _P]),
+    "turtle_ecef_from_geodetic_batch_device": (_I, [_N, _P, _P, _P, _P, _P]),
+    "turtle_ecef_from_horizontal_batch": (_I, [_N, _P, _P, _P, _P, _P]),
+    "turtle_ecef_from_horizontal_batch_device": (_I, [_N, _P, _P, _P, _P, _P, _P]),
+    # elevation
+    "turtle_map_elevation_batch": (_I, [_P, _N, _P, _P, _P, _P]),
+    "turtle_map_elevation_batch_device": (_I, [_P, _N, _P, _P, _P, _P, _P]),
+    "turtle_map_elevation_ecef_batch": (_I, [_P, _N, _P, _P, _P, _P, _P, _P]),
+    "turtle_map_elevation_ecef_batch_device": (_I, [_P, _N, _P, _P, _P, _P, _P, _P, _P]),
+    "turtle_map_fill_batch": (_I, [_P, _P]),
+    # utilities
+    "turtle_b200_device_count": (_I, []),
+    "turtle_b200_dfma_peak": (_D, [_I]),
+    "turtle_b200_version": (C.c_char_p, []),
+}
+
+
+def load(path=LIB_PATH):
+    """Load the shared library and attach the signatures. Raises if it is absent."""
+    if not os.path.exists(path):
+        raise ImportError(
+            "%s is missing: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (nvcc, sm_100a). turtle_b200 has no Python/CPU fallback." % path)
+    lib = C.CDLL(path, mode=getattr(os, "RTLD_LOCAL", 0) | getattr(os, "RTLD_NOW", 2))
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    return lib
+
+
+lib = load()

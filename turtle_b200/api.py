@@ -1,0 +1,399 @@
+"""Thin Python mirror of the C interface (turtle.h + turtle_b200.h), for tests and
+bench.py. Names follow the C objects: Map, Stack, Stepper, Plan, States.
+
+numpy arrays are passed as HOST pointers (the ``*_batch`` calls), torch CUDA
+tensors as DEVICE pointers (the ``*_batch_device`` calls). Nothing is computed in
+Python.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import (ERROR_HANDLER, MapInfo, PlanCounters, TraceRule, lib)
+
+TRACE_RESULT = np.dtype([
+    ("position", "<f8", (3,)), ("altitude", "<f8"), ("length", "<f8", (4,)),
+    ("total", "<f8"), ("n_steps", "<i4"), ("status", "<i4"), ("index", "<i4", (2,)),
+    ("medium_hash", "<u4"), ("n_changes", "<i4")])
+assert TRACE_RESULT.itemsize == 96
+
+TRACE_ALTITUDE, TRACE_DOMAIN, TRACE_LENGTH, TRACE_STEPS, TRACE_INVALID = range(5)
+
+
+class TurtleError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(message)
+        self.code = code
+
+
+_last_error = []
+
+
+@ERROR_HANDLER
+def _on_error(code, function, message):
+    _last_error.append((code, message.decode() if message else ""))
+
+
+lib.turtle_error_handler_set(C.cast(_on_error, C.c_void_p))
+
+
+def _check(rc):
+    if rc != 0:
+        code, message = _last_error.pop() if _last_error else (rc, "turtle error %d" % rc)
+        del _last_error[:]
+        raise TurtleError(code, message)
+    del _last_error[:]
+
+
+def _f8(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _ptr(a):
+    """Host pointer of a numpy array, device pointer of a torch tensor, or NULL."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(a.data_ptr())
+
+
+def device_count():
+    return lib.turtle_b200_device_count()
+
+
+def dfma_peak(repeats=3):
+    return lib.turtle_b200_dfma_peak(repeats)
+
+
+# ---- frames -------------------------------------------------------------------
+
+def ecef_from_geodetic(latitude, longitude, elevation):
+    out = (C.c_double * 3)()
+    lib.turtle_ecef_from_geodetic(latitude, longitude, elevation, out)
+    return np.array(out)
+
+
+def ecef_to_geodetic(ecef):
+    e = (C.c_double * 3)(*ecef)
+    la, lo, al = C.c_double(), C.c_double(), C.c_double()
+    lib.turtle_ecef_to_geodetic(e, C.byref(la), C.byref(lo), C.byref(al))
+    return la.value, lo.value, al.value
+
+
+def ecef_from_horizontal(latitude, longitude, azimuth, elevation):
+    out = (C.c_double * 3)()
+    lib.turtle_ecef_from_horizontal(latitude, longitude, azimuth, elevation, out)
+    return np.array(out)
+
+
+def ecef_to_geodetic_batch(ecef):
+    ecef = _f8(ecef, (-1, 3))
+    n = len(ecef)
+    la, lo, al = np.empty(n), np.empty(n), np.empty(n)
+    _check(lib.turtle_ecef_to_geodetic_batch(n, _ptr(ecef), _ptr(la), _ptr(lo), _ptr(al)))
+    return la, lo, al
+
+
+def ecef_from_geodetic_batch(latitude, longitude, elevation):
+    la, lo, el = _f8(latitude), _f8(longitude), _f8(elevation)
+    out = np.empty((len(la), 3))
+    _check(lib.turtle_ecef_from_geodetic_batch(len(la), _ptr(la), _ptr(lo), _ptr(el), _ptr(out)))
+    return out
+
+
+def ecef_from_horizontal_batch(latitude, longitude, azimuth, elevation):
+    la, lo, az, el = _f8(latitude), _f8(longitude), _f8(azimuth), _f8(elevation)
+    out = np.empty((len(la), 3))
+    _check(lib.turtle_ecef_from_horizontal_batch(
+        len(la), _ptr(la), _ptr(lo), _ptr(az), _ptr(el), _ptr(out)))
+    return out
+
+
+# ---- objects --------------------------------------------------------------------
+
+class Projection:
+    def __init__(self, name):
+        self._p = C.c_void_p()
+        _check(lib.turtle_projection_create(C.byref(self._p), name.encode()))
+
+    def project(self, latitude, longitude):
+        x, y = C.c_double(), C.c_double()
+        _check(lib.turtle_projection_project(self._p, latitude, longitude, C.byref(x), C.byref(y)))
+        return x.value, y.value
+
+    def unproject(self, x, y):
+        la, lo = C.c_double(), C.c_double()
+        _check(lib.turtle_projection_unproject(self._p, x, y, C.byref(la), C.byref(lo)))
+        return la.value, lo.value
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            lib.turtle_projection_destroy(C.byref(self._p))
+
+
+class Map:
+    """turtle_map: 16-bit node grid. ``values[iy, ix]`` fills every node."""
+
+    def __init__(self, nx=None, ny=None, x=None, y=None, z=None, projection=None,
+                 values=None, path=None):
+        self._p = C.c_void_p()
+        if path is not None:
+            _check(lib.turtle_map_load(C.byref(self._p), path.encode()))
+            return
+        info = MapInfo(nx, ny, (C.c_double * 2)(*x), (C.c_double * 2)(*y),
+                       (C.c_double * 2)(*z), None)
+        _check(lib.turtle_map_create(C.byref(self._p), C.byref(info),
+                                     projection.encode() if projection else None))
+        if values is not None:
+            self.fill(values)
+
+    @property
+    def handle(self):
+        return self._p
+
+    def fill(self, values):
+        v = _f8(values)
+        _check(lib.turtle_map_fill_batch(self._p, _ptr(v)))
+
+    def meta(self):
+        info = MapInfo()
+        name = C.c_char_p()
+        lib.turtle_map_meta(self._p, C.byref(info), C.byref(name))
+        return info, (name.value.decode() if name.value else None)
+
+    def node(self, ix, iy):
+        x, y, z = C.c_double(), C.c_double(), C.c_double()
+        _check(lib.turtle_map_node(self._p, ix, iy, C.byref(x), C.byref(y), C.byref(z)))
+        return x.value, y.value, z.value
+
+    def elevation(self, x, y):
+        z, inside = C.c_double(), C.c_int()
+        _check(lib.turtle_map_elevation(self._p, x, y, C.byref(z), C.byref(inside)))
+        return z.value, inside.value
+
+    def elevation_batch(self, x, y):
+        x, y = _f8(x), _f8(y)
+        z = np.zeros(len(x))
+        inside = np.zeros(len(x), dtype=np.int32)
+        _check(lib.turtle_map_elevation_batch(self._p, len(x), _ptr(x), _ptr(y), _ptr(z),
+                                              _ptr(inside)))
+        return z, inside
+
+    def elevation_ecef_batch(self, ecef):
+        ecef = _f8(ecef, (-1, 3))
+        n = len(ecef)
+        la, lo, al, z = np.empty(n), np.empty(n), np.empty(n), np.zeros(n)
+        inside = np.zeros(n, dtype=np.int32)
+        _check(lib.turtle_map_elevation_ecef_batch(
+            self._p, n, _ptr(ecef), _ptr(la), _ptr(lo), _ptr(al), _ptr(z), _ptr(inside)))
+        return la, lo, al, z, inside
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            lib.turtle_map_destroy(C.byref(self._p))
+
+
+class Stack:
+    """turtle_stack over a directory of `.hgt` tiles."""
+
+    def __init__(self, path, size=0):
+        self._p = C.c_void_p()
+        _check(lib.turtle_stack_create(C.byref(self._p), path.encode(), size, None, None))
+
+    @property
+    def handle(self):
+        return self._p
+
+    def load(self):
+        _check(lib.turtle_stack_load(self._p))
+
+    def elevation(self, latitude, longitude):
+        z, inside = C.c_double(), C.c_int()
+        _check(lib.turtle_stack_elevation(self._p, latitude, longitude, C.byref(z),
+                                          C.byref(inside)))
+        return z.value, inside.value
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            lib.turtle_stack_destroy(C.byref(self._p))
+
+
+class Stepper:
+    """turtle_stepper: geometry description + tunables (+ scalar set-up calls)."""
+
+    def __init__(self, range=None, slope=None, resolution=None, geoid=None):
+        self._p = C.c_void_p()
+        self._keep = []
+        _check(lib.turtle_stepper_create(C.byref(self._p)))
+        if geoid is not None:
+            self._keep.append(geoid)
+            lib.turtle_stepper_geoid_set(self._p, geoid.handle)
+        if slope is not None:
+            lib.turtle_stepper_slope_set(self._p, slope)
+        if resolution is not None:
+            lib.turtle_stepper_resolution_set(self._p, resolution)
+        if range is not None:
+            lib.turtle_stepper_range_set(self._p, range)
+
+    @property
+    def handle(self):
+        return self._p
+
+    def add_layer(self):
+        _check(lib.turtle_stepper_add_layer(self._p))
+
+    def add_flat(self, offset=0.):
+        _check(lib.turtle_stepper_add_flat(self._p, offset))
+
+    def add_map(self, map_, offset=0.):
+        self._keep.append(map_)
+        _check(lib.turtle_stepper_add_map(self._p, map_.handle, offset))
+
+    def add_stack(self, stack, offset=0.):
+        self._keep.append(stack)
+        _check(lib.turtle_stepper_add_stack(self._p, stack.handle, offset))
+
+    def reset(self):
+        lib.turtle_stepper_reset(self._p)
+
+    def position(self, latitude, longitude, height, layer):
+        pos = (C.c_double * 3)()
+        index = C.c_int()
+        _check(lib.turtle_stepper_position(self._p, latitude, longitude, height, layer, pos,
+                                           C.byref(index)))
+        return np.array(pos), index.value
+
+    def step(self, position, direction=None):
+        """Scalar turtle_stepper_step (host, set-up path). Returns a dict."""
+        pos = (C.c_double * 3)(*position)
+        d = (C.c_double * 3)(*direction) if direction is not None else None
+        la, lo, al, st = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        el = (C.c_double * 2)()
+        idx = (C.c_int * 2)()
+        _check(lib.turtle_stepper_step(self._p, pos, d, C.byref(la), C.byref(lo), C.byref(al),
+                                       el, C.byref(st), idx))
+        return dict(position=np.array(pos), latitude=la.value, longitude=lo.value,
+                    altitude=al.value, elevation=(el[0], el[1]), step=st.value,
+                    index=(idx[0], idx[1]))
+
+    def freeze(self, device=0):
+        return Plan(self, device)
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            lib.turtle_stepper_destroy(C.byref(self._p))
+
+
+def trace_rule(altitude_max, altitude_min=-1.7976931348623157e308,
+               length_max=1.7976931348623157e308, max_steps=100000):
+    return TraceRule(altitude_min, altitude_max, length_max, max_steps, 0)
+
+
+class Plan:
+    """turtle_plan: a stepper geometry resident on one GPU."""
+
+    def __init__(self, stepper, device=0):
+        self._p = C.c_void_p()
+        self.stepper = stepper
+        _check(lib.turtle_stepper_freeze(stepper.handle, device, C.byref(self._p)))
+
+    @property
+    def handle(self):
+        return self._p
+
+    @property
+    def device(self):
+        return lib.turtle_plan_device(self._p)
+
+    @property
+    def bytes(self):
+        return lib.turtle_plan_bytes(self._p)
+
+    def launch_set(self, ctas_per_sm=0, threads=0):
+        lib.turtle_plan_launch_set(self._p, ctas_per_sm, threads)
+
+    def counters(self, sync=False):
+        if sync:
+            lib.turtle_plan_counters_sync(self._p)
+        c = PlanCounters()
+        lib.turtle_plan_counters_get(self._p, C.byref(c))
+        return dict(rays=c.rays, steps=c.steps, samples=c.samples, launches=c.launches,
+                    kernel_ms=c.kernel_ms)
+
+    def trace(self, position, direction, rule, results=None):
+        """Host arrays in, host records out (turtle_stepper_trace_batch)."""
+        position, direction = _f8(position, (-1, 3)), _f8(direction, (-1, 3))
+        n = len(position)
+        if results is None:
+            results = np.zeros(n, dtype=TRACE_RESULT)
+        _check(lib.turtle_stepper_trace_batch(self._p, n, _ptr(position), _ptr(direction),
+                                              C.byref(rule), _ptr(results)))
+        return results
+
+    def trace_device(self, n, position, direction, rule, results, stream=None):
+        """Device tensors in / out (turtle_stepper_trace_batch_device), asynchronous."""
+        _check(lib.turtle_stepper_trace_batch_device(
+            self._p, n, _ptr(position), _ptr(direction), C.byref(rule), _ptr(results),
+            C.c_void_p(stream) if stream else None))
+
+    def step(self, position, direction=None, states=None):
+        """One turtle_stepper_step per particle, host arrays. Returns a dict of arrays;
+        ``position`` is advanced in place when a direction is given."""
+        position = _f8(position, (-1, 3))
+        n = len(position)
+        d = _f8(direction, (-1, 3)) if direction is not None else None
+        out = dict(position=position, latitude=np.empty(n), longitude=np.empty(n),
+                   altitude=np.empty(n), elevation=np.empty((n, 2)), step=np.empty(n),
+                   index=np.empty((n, 2), dtype=np.int32))
+        _check(lib.turtle_stepper_step_batch(
+            self._p, states.handle if states else None, n, _ptr(position), _ptr(d),
+            _ptr(out["latitude"]), _ptr(out["longitude"]), _ptr(out["altitude"]),
+            _ptr(out["elevation"]), _ptr(out["step"]), _ptr(out["index"])))
+        return out
+
+    def step_device(self, n, position, direction, states=None, latitude=None,
+                    longitude=None, altitude=None, elevation=None, step=None, index=None,
+                    stream=None):
+        _check(lib.turtle_stepper_step_batch_device(
+            self._p, states.handle if states else None, n, _ptr(position), _ptr(direction),
+            _ptr(latitude), _ptr(longitude), _ptr(altitude), _ptr(elevation), _ptr(step),
+            _ptr(index), C.c_void_p(stream) if stream else None))
+
+    def position(self, latitude, longitude, height, layer):
+        la, lo, h = _f8(latitude), _f8(longitude), _f8(height)
+        pos = np.zeros((len(la), 3))
+        idx = np.empty(len(la), dtype=np.int32)
+        _check(lib.turtle_stepper_position_batch(self._p, len(la), _ptr(la), _ptr(lo), _ptr(h),
+                                                 layer, _ptr(pos), _ptr(idx)))
+        return pos, idx
+
+    def states(self, n):
+        return States(self, n)
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            lib.turtle_plan_destroy(C.byref(self._p))
+
+
+class States:
+    """turtle_states: per-particle stepper memory on the device."""
+
+    def __init__(self, plan, n):
+        self._p = C.c_void_p()
+        self.plan = plan
+        _check(lib.turtle_states_create(plan.handle, n, C.byref(self._p)))
+
+    @property
+    def handle(self):
+        return self._p
+
+    def reset(self):
+        _check(lib.turtle_states_reset(self._p))
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            lib.turtle_states_destroy(C.byref(self._p))

@@ -1,0 +1,1366 @@
+/*
+ * tb_kernels.cu -- sm_100a kernels and the batched C ABI of turtle-b200.
+ *
+ * Hot path: turtle_stepper_step (ref: src/turtle/stepper.c:780-875) for millions
+ * of independent rays. Design (DESIGN.md has the full story):
+ *
+ *  - one ray per lane, persistent CTAs sized to the SM count, rays pulled from a
+ *    global cursor; finished lanes are refilled with a warp ballot/popc
+ *    compaction so that heavy-tailed rays do not idle their warp;
+ *  - the unit of lockstep work is the geometry SAMPLE, not the step: each loop
+ *    iteration evaluates exactly one stepper_sample (geodetic transform ->
+ *    projection -> 2x2 gather) for every lane, then a branch-light update of a
+ *    three-state machine {INIT, TENTATIVE, BISECT}. The 23-iteration boundary
+ *    bisection of one lane therefore costs its warp nothing extra;
+ *  - DEM tiles are int16/uint16 grids resident in HBM, rows south first with a
+ *    32-byte aligned pitch; the flattened geometry travels as a __grid_constant__
+ *    kernel parameter (constant bank), map descriptors and the tile table sit in
+ *    global memory behind the read-only cache;
+ *  - FP64 throughout, compiled with -fmad=false: see tb_core.cuh.
+ *
+ * No tensor cores: the path is FP64-pipe / issue bound (DESIGN.md roofline).
+ */
+#include <cuda_runtime.h>
+
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "tb_host.hpp"
+#include "turtle_b200.h"
+
+#define FN(f) ((turtle_function_t *)(f))
+static const char * BATCH_CU = "turtle_b200/csrc/tb_kernels.cu";
+
+#define CUDA_TRY(fn, call)                                                         \
+        do {                                                                       \
+                cudaError_t err_ = (call);                                         \
+                if (err_ != cudaSuccess)                                           \
+                        return tbh::raise(FN(fn), TURTLE_RETURN_LIBRARY_ERROR,     \
+                            BATCH_CU, __LINE__, "CUDA error: %s (%s)",             \
+                            cudaGetErrorString(err_), #call);                      \
+        } while (0)
+
+/* ======================================================================== */
+/* Device code                                                               */
+/* ======================================================================== */
+
+namespace {
+
+enum { MODE_IDLE = 0, MODE_INIT = 1, MODE_TENT = 2, MODE_BISECT = 3 };
+
+struct TraceArgs {
+        unsigned long long n;
+        const double * position;
+        const double * direction;
+        turtle_trace_result * results;
+        unsigned long long * cursor; /* [0] next ray, [1] steps, [2] samples */
+        double altitude_min, altitude_max, length_max;
+        int max_steps;
+};
+
+__device__ __forceinline__ bool finite3(const double v[3])
+{
+        return isfinite(v[0]) && isfinite(v[1]) && isfinite(v[2]);
+}
+
+/* The persistent ray-tracing kernel. */
+template <bool LLA>
+__global__ void __launch_bounds__(128)
+    trace_kernel(const __grid_constant__ tb::Geometry G, const TraceArgs A)
+{
+        const unsigned lane = threadIdx.x & 31u;
+        const unsigned FULL = 0xffffffffu;
+
+        /* lane state: one ray */
+        double pos[3] = { 0., 0., 0. }, dir[3] = { 0., 0., 0. };
+        tb::Sample last;
+        last.lat = last.lon = last.alt = last.elev0 = last.elev1 = 0.;
+        last.idx0 = last.idx1 = -1;
+        double ds = 0., ds0 = 0., ds1 = 0.;
+        double len[TURTLE_TRACE_MEDIA] = { 0., 0., 0., 0. };
+        double total = 0.;
+        int medium0 = -1, mode = MODE_IDLE;
+        int n_steps = 0, n_changes = 0;
+        unsigned hash = 0u;
+        unsigned long long ray = 0ull;
+        double last_pos[3] = { DBL_MAX, DBL_MAX, DBL_MAX };
+        tb::LlaState lla[LLA ? tb::MAX_TRANSFORMS : 1];
+
+        unsigned long long my_steps = 0ull, my_samples = 0ull;
+        bool exhausted = false;
+
+        for (;;) {
+                /* ---- refill idle lanes from the global ray queue ---------- */
+                const unsigned idle = __ballot_sync(FULL, mode == MODE_IDLE);
+                if (idle != 0u) {
+                        if (!exhausted) {
+                                const int need = __popc(idle);
+                                unsigned long long base = 0ull;
+                                if (lane == 0u)
+                                        base = atomicAdd(A.cursor, (unsigned long long)need);
+                                base = __shfl_sync(FULL, base, 0);
+                                if (mode == MODE_IDLE) {
+                                        const unsigned rank = __popc(idle & ((1u << lane) - 1u));
+                                        const unsigned long long r = base + rank;
+                                        if (r < A.n) {
+                                                ray = r;
+                                                const double * p = A.position + 3ull * r;
+                                                const double * d = A.direction + 3ull * r;
+                                                pos[0] = p[0]; pos[1] = p[1]; pos[2] = p[2];
+                                                dir[0] = d[0]; dir[1] = d[1]; dir[2] = d[2];
+                                                len[0] = len[1] = len[2] = len[3] = 0.;
+                                                total = 0.;
+                                                n_steps = n_changes = 0;
+                                                mode = MODE_INIT;
+                                                /* every ray starts from a reset stepper
+                                                 * (turtle_stepper_reset, stepper.c:647-651) */
+                                                last_pos[0] = last_pos[1] = last_pos[2] = DBL_MAX;
+                                                if (LLA) tb::lla_reset(lla, G.n_transforms);
+                                                if (!finite3(pos) || !finite3(dir)) {
+                                                        turtle_trace_result * R = A.results + r;
+                                                        R->position[0] = pos[0];
+                                                        R->position[1] = pos[1];
+                                                        R->position[2] = pos[2];
+                                                        R->altitude = 0.;
+                                                        R->length[0] = R->length[1] = 0.;
+                                                        R->length[2] = R->length[3] = 0.;
+                                                        R->total = 0.;
+                                                        R->n_steps = 0;
+                                                        R->status = TURTLE_TRACE_INVALID;
+                                                        R->index[0] = R->index[1] = -1;
+                                                        R->medium_hash = 0u;
+                                                        R->n_changes = 0;
+                                                        mode = MODE_IDLE;
+                                                }
+                                        }
+                                }
+                                if (base + (unsigned long long)need >= A.n) exhausted = true;
+                        }
+                        if (__all_sync(FULL, mode == MODE_IDLE)) {
+                                if (exhausted) break;
+                                continue;
+                        }
+                }
+                if (mode == MODE_IDLE) continue;
+
+                /* ---- exactly one geometry sample per lane and iteration ---- */
+                double p[3];
+                double ds2 = 0.;
+                if (mode == MODE_INIT) {
+                        p[0] = pos[0]; p[1] = pos[1]; p[2] = pos[2];
+                } else if (mode == MODE_TENT) { /* stepper.c:824 */
+                        p[0] = pos[0] + dir[0] * ds;
+                        p[1] = pos[1] + dir[1] * ds;
+                        p[2] = pos[2] + dir[2] * ds;
+                } else { /* stepper.c:840-844 */
+                        ds2 = 0.5 * (ds0 + ds1);
+                        p[0] = pos[0] + dir[0] * ds2;
+                        p[1] = pos[1] + dir[1] * ds2;
+                        p[2] = pos[2] + dir[2] * ds2;
+                }
+                tb::Sample S;
+                tb::sample_geometry<LLA>(G, lla, last_pos, mode != MODE_BISECT, p, S);
+                my_samples++;
+
+                /* ---- state update ------------------------------------------ */
+                bool settle = false;  /* a step (or the initial query) completed */
+                if (mode == MODE_INIT) {
+                        last = S;
+                        hash = (2166136261u ^ (unsigned)(S.idx0 + 1)) * 16777619u;
+                        settle = true;
+                } else if (mode == MODE_TENT) {
+                        pos[0] = p[0]; pos[1] = p[1]; pos[2] = p[2];
+                        last = S;
+                        if (S.idx0 != medium0) { /* stepper.c:832-838 */
+                                ds0 = -ds;
+                                ds1 = 0.;
+                                mode = MODE_BISECT;
+                                settle = !(ds1 - ds0 > 1E-08);
+                        } else {
+                                settle = true;
+                        }
+                } else {
+                        if (S.idx0 == medium0) { /* stepper.c:848-859 */
+                                ds0 = ds2;
+                        } else {
+                                ds1 = ds2;
+                                last = S;
+                                last_pos[0] = p[0]; last_pos[1] = p[1]; last_pos[2] = p[2];
+                        }
+                        if (!(ds1 - ds0 > 1E-08)) { /* stepper.c:861-863 */
+                                ds += ds1;
+                                pos[0] += dir[0] * ds1;
+                                pos[1] += dir[1] * ds1;
+                                pos[2] += dir[2] * ds1;
+                                settle = true;
+                        }
+                }
+                if (!settle) continue;
+
+                if (mode != MODE_INIT) {
+                        /* example-stepper.c:136-139: length by STARTING medium */
+                        const int m = (medium0 < TURTLE_TRACE_MEDIA - 1) ? medium0 :
+                                                                           TURTLE_TRACE_MEDIA - 1;
+                        if (m == 0) len[0] += ds;
+                        else if (m == 1) len[1] += ds;
+                        else if (m == 2) len[2] += ds;
+                        else len[3] += ds;
+                        total += ds;
+                        n_steps++;
+                        my_steps++;
+                        if (last.idx0 != medium0) {
+                                n_changes++;
+                                hash = (hash ^ (unsigned)(last.idx0 + 1)) * 16777619u;
+                        }
+                }
+
+                int status = -1;
+                if (last.idx0 < 0)
+                        status = TURTLE_TRACE_DOMAIN;
+                else if (!(last.alt < A.altitude_max) || !(last.alt > A.altitude_min))
+                        status = TURTLE_TRACE_ALTITUDE;
+                else if (total >= A.length_max)
+                        status = TURTLE_TRACE_LENGTH;
+                else if (n_steps >= A.max_steps)
+                        status = TURTLE_TRACE_STEPS;
+
+                if (status >= 0) {
+                        turtle_trace_result * R = A.results + ray;
+                        R->position[0] = pos[0];
+                        R->position[1] = pos[1];
+                        R->position[2] = pos[2];
+                        R->altitude = last.alt;
+                        R->length[0] = len[0];
+                        R->length[1] = len[1];
+                        R->length[2] = len[2];
+                        R->length[3] = len[3];
+                        R->total = total;
+                        R->n_steps = n_steps;
+                        R->status = status;
+                        R->index[0] = last.idx0;
+                        R->index[1] = last.idx1;
+                        R->medium_hash = hash;
+                        R->n_changes = n_changes;
+                        mode = MODE_IDLE;
+                } else {
+                        medium0 = last.idx0;
+                        ds = tb::step_length(G, last); /* stepper.c:798-813 */
+                        mode = MODE_TENT;
+                }
+        }
+
+        /* per-warp counters */
+        for (int o = 16; o > 0; o >>= 1) {
+                my_steps += __shfl_down_sync(FULL, my_steps, o);
+                my_samples += __shfl_down_sync(FULL, my_samples, o);
+        }
+        if (lane == 0u) {
+                atomicAdd(A.cursor + 1, my_steps);
+                atomicAdd(A.cursor + 2, my_samples);
+        }
+}
+
+/* Device-side particle state of turtle_stepper_step_batch. */
+struct ParticleState {
+        tb::StepperState st;
+        tb::LlaState lla[tb::MAX_TRANSFORMS];
+};
+
+struct StepArgs {
+        unsigned long long n;
+        ParticleState * states; /* or NULL */
+        double * position;
+        const double * direction; /* or NULL: query mode */
+        double * latitude;
+        double * longitude;
+        double * altitude;
+        double * elevation;
+        double * step;
+        int * index;
+        unsigned long long * counters; /* [1] steps */
+};
+
+/* One turtle_stepper_step per particle (ref: stepper.c:780-875). */
+template <bool LLA>
+__global__ void __launch_bounds__(128)
+    step_kernel(const __grid_constant__ tb::Geometry G, const StepArgs A)
+{
+        const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+             i < A.n; i += stride) {
+                ParticleState local;
+                ParticleState * ps = &local;
+                if (A.states != NULL)
+                        ps = A.states + i;
+                else
+                        tb::state_reset(local.st, local.lla, G.n_transforms);
+                double pos[3] = { A.position[3 * i], A.position[3 * i + 1],
+                        A.position[3 * i + 2] };
+                double dir[3] = { 0., 0., 0. };
+                const double * d = NULL;
+                if (A.direction != NULL) {
+                        dir[0] = A.direction[3 * i];
+                        dir[1] = A.direction[3 * i + 1];
+                        dir[2] = A.direction[3 * i + 2];
+                        d = dir;
+                }
+                const double ds = tb::stepper_step<LLA>(G, ps->lla, ps->st, pos, d);
+                const tb::Sample & last = ps->st.last;
+                if (d != NULL) {
+                        A.position[3 * i] = pos[0];
+                        A.position[3 * i + 1] = pos[1];
+                        A.position[3 * i + 2] = pos[2];
+                }
+                if (A.latitude != NULL) A.latitude[i] = last.lat;
+                if (A.longitude != NULL) A.longitude[i] = last.lon;
+                if (A.altitude != NULL) A.altitude[i] = last.alt;
+                if (A.elevation != NULL) { /* stepper.c:765-772 */
+                        A.elevation[2 * i] = (last.idx0 >= 0) ? last.elev0 : 0.;
+                        A.elevation[2 * i + 1] = (last.idx0 >= 0) ? last.elev1 : 0.;
+                }
+                if (A.step != NULL) A.step[i] = ds;
+                if (A.index != NULL) {
+                        A.index[2 * i] = last.idx0;
+                        A.index[2 * i + 1] = last.idx1;
+                }
+        }
+}
+
+__global__ void states_reset_kernel(ParticleState * states, unsigned long long n)
+{
+        const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+             i < n; i += stride) {
+                tb::state_reset(states[i].st, states[i].lla, tb::MAX_TRANSFORMS);
+                states[i].st.last.idx0 = states[i].st.last.idx1 = -1;
+                states[i].st.last.lat = states[i].st.last.lon = states[i].st.last.alt = 0.;
+                states[i].st.last.elev0 = states[i].st.last.elev1 = 0.;
+        }
+}
+
+/* ref: turtle_stepper_position, stepper.c:877-931 */
+__global__ void position_kernel(const __grid_constant__ tb::Geometry G,
+    unsigned long long n, const double * latitude, const double * longitude,
+    const double * height, int layer_index, double * position, int * data_index)
+{
+        const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+        const tb::LayerDesc layer = G.layers[layer_index];
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+             i < n; i += stride) {
+                const double la = latitude[i], lo = longitude[i];
+                int found = -1;
+                for (int k = 0; k < layer.n; k++) {
+                        const tb::MetaDesc & meta = G.metas[layer.first + k];
+                        const tb::DataDesc & d = G.data[meta.data];
+                        double z = 0.;
+                        int inside;
+                        if (d.kind == tb::DATA_FLAT) {
+                                inside = 1;
+                        } else if (d.kind == tb::DATA_STACK) {
+                                inside = tb::stack_elevation(G, G.stacks[d.ref], la, lo, z);
+                        } else if (G.transforms[d.transform].type != tb::PROJ_GEODETIC) {
+                                double x, y;
+                                tb::project(G.transforms[d.transform], la, lo, x, y);
+                                inside = tb::map_elevation(G.maps[d.ref], x, y, z);
+                        } else {
+                                inside = tb::map_elevation(G.maps[d.ref], lo, la, z);
+                        }
+                        if (!inside) continue;
+                        z += meta.offset;
+                        if (G.geoid >= 0) {
+                                const double l360 = (lo >= 0) ? lo : lo + 360.;
+                                double undulation;
+                                if (tb::map_elevation(G.maps[G.geoid], l360, la, undulation))
+                                        z += undulation;
+                        }
+                        double ecef[3];
+                        tb::ecef_from_geodetic(la, lo, z + height[i], ecef);
+                        position[3 * i] = ecef[0];
+                        position[3 * i + 1] = ecef[1];
+                        position[3 * i + 2] = ecef[2];
+                        found = k;
+                        break;
+                }
+                if (data_index != NULL) data_index[i] = found;
+        }
+}
+
+/* ---- frame transform kernels (ref: ecef.c) -------------------------------- */
+
+__global__ void __launch_bounds__(256) to_geodetic_kernel(unsigned long long n,
+    const double * __restrict__ ecef, double * __restrict__ latitude,
+    double * __restrict__ longitude, double * __restrict__ altitude)
+{
+        const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+             i < n; i += stride) {
+                const double r[3] = { ecef[3 * i], ecef[3 * i + 1], ecef[3 * i + 2] };
+                double la, lo, al;
+                tb::ecef_to_geodetic(r, la, lo, al);
+                if (latitude != NULL) latitude[i] = la;
+                if (longitude != NULL) longitude[i] = lo;
+                if (altitude != NULL) altitude[i] = al;
+        }
+}
+
+__global__ void __launch_bounds__(256) from_geodetic_kernel(unsigned long long n,
+    const double * __restrict__ latitude, const double * __restrict__ longitude,
+    const double * __restrict__ elevation, double * __restrict__ ecef)
+{
+        const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+             i < n; i += stride) {
+                double r[3];
+                tb::ecef_from_geodetic(latitude[i], longitude[i], elevation[i], r);
+                ecef[3 * i] = r[0];
+                ecef[3 * i + 1] = r[1];
+                ecef[3 * i + 2] = r[2];
+        }
+}
+
+__global__ void __launch_bounds__(256) from_horizontal_kernel(unsigned long long n,
+    const double * __restrict__ latitude, const double * __restrict__ longitude,
+    const double * __restrict__ azimuth, const double * __restrict__ elevation,
+    double * __restrict__ direction)
+{
+        const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+             i < n; i += stride) {
+                double r[3];
+                tb::ecef_from_horizontal(latitude[i], longitude[i], azimuth[i], elevation[i], r);
+                direction[3 * i] = r[0];
+                direction[3 * i + 1] = r[1];
+                direction[3 * i + 2] = r[2];
+        }
+}
+
+/* ---- elevation kernels (ref: map.c:229-277) -------------------------------- */
+
+__global__ void __launch_bounds__(256) map_elevation_kernel(const tb::MapDesc M,
+    unsigned long long n, const double * __restrict__ x, const double * __restrict__ y,
+    double * __restrict__ z, int * __restrict__ inside)
+{
+        const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+             i < n; i += stride) {
+                double zi;
+                const int in = tb::map_elevation(M, x[i], y[i], zi);
+                if (in) z[i] = zi;
+                if (inside != NULL) inside[i] = in;
+        }
+}
+
+/* ECEF -> geodetic -> (projection) -> bilinear, fused: 24 B in, up to 36 B out
+ * per point, nothing intermediate in HBM. */
+__global__ void __launch_bounds__(256) map_elevation_ecef_kernel(const tb::MapDesc M,
+    const tb::ProjDesc P, unsigned long long n, const double * __restrict__ ecef,
+    double * __restrict__ latitude, double * __restrict__ longitude,
+    double * __restrict__ altitude, double * __restrict__ z, int * __restrict__ inside)
+{
+        const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+             i < n; i += stride) {
+                const double r[3] = { ecef[3 * i], ecef[3 * i + 1], ecef[3 * i + 2] };
+                double la, lo, al;
+                tb::ecef_to_geodetic(r, la, lo, al);
+                double mx = lo, my = la;
+                if (P.type != tb::PROJ_GEODETIC) tb::project(P, la, lo, mx, my);
+                double zi;
+                const int in = tb::map_elevation(M, mx, my, zi);
+                if (latitude != NULL) latitude[i] = la;
+                if (longitude != NULL) longitude[i] = lo;
+                if (altitude != NULL) altitude[i] = al;
+                if (in) z[i] = zi;
+                if (inside != NULL) inside[i] = in;
+        }
+}
+
+/* ---- FP64 FMA peak (roofline denominator of the stepper) --------------------- */
+
+__global__ void __launch_bounds__(256) dfma_kernel(double * out, int iterations)
+{
+        double a0 = threadIdx.x * 1e-9, a1 = a0 + 1., a2 = a0 + 2., a3 = a0 + 3.;
+        double a4 = a0 + 4., a5 = a0 + 5., a6 = a0 + 6., a7 = a0 + 7.;
+        const double b = 1.0000001, c = 1e-7;
+        for (int i = 0; i < iterations; i++) {
+                a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+                a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+        }
+        out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] =
+            a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+} /* namespace */
+
+/* ======================================================================== */
+/* Host side: plans, residency, launches                                     */
+/* ======================================================================== */
+
+namespace {
+const int N_SLOTS = 3;              /* host-pointer pipeline depth */
+const size_t CHUNK_RAYS = 1u << 20; /* rays per pipeline chunk */
+}
+
+struct turtle_plan {
+        int device;
+        int sm_count;
+        int ctas_per_sm, threads;
+        tb::Geometry G; /* device pointers */
+        void * pool;    /* every tile of the plan, one allocation */
+        tb::MapDesc * d_maps;
+        int * d_tiles;
+        size_t bytes;
+        std::vector<struct turtle_stack *> pinned;
+        unsigned long long * d_counters; /* N_SLOTS + 1 triplets */
+        turtle_plan_counters counters;
+        /* host-pointer pipeline */
+        cudaStream_t stream[N_SLOTS];
+        cudaEvent_t ev0[N_SLOTS], ev1[N_SLOTS];
+        double * d_in[N_SLOTS];
+        turtle_trace_result * d_out[N_SLOTS];
+        size_t slot_rays;
+};
+
+struct turtle_states {
+        struct turtle_plan * plan;
+        size_t n;
+        ParticleState * d_states;
+};
+
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+static enum turtle_return require_device(turtle_function_t * fn, int device)
+{
+        int count = 0;
+        cudaError_t err = cudaGetDeviceCount(&count);
+        if ((err != cudaSuccess) || (count == 0)) {
+                cudaGetLastError();
+                return tbh::raise(fn, TURTLE_RETURN_LIBRARY_ERROR, BATCH_CU, __LINE__,
+                    "no CUDA device: the batched path has no CPU fallback (%s)",
+                    (err != cudaSuccess) ? cudaGetErrorString(err) : "0 devices");
+        }
+        if ((device < 0) || (device >= count))
+                return tbh::raise(fn, TURTLE_RETURN_DOMAIN_ERROR, BATCH_CU, __LINE__,
+                    "invalid device %d (have %d)", device, count);
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" int turtle_b200_device_count(void)
+{
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess) {
+                cudaGetLastError();
+                return 0;
+        }
+        return count;
+}
+
+extern "C" const char * turtle_b200_version(void) { return "turtle-b200 0.1 (sm_100a)"; }
+
+/* Copy a host grid into the device pool with a padded pitch. */
+static cudaError_t upload_nodes(uint16_t * dst, int pitch, const struct turtle_map * map)
+{
+        return cudaMemcpy2D(dst, (size_t)pitch * sizeof(uint16_t), map->nodes.data(),
+            (size_t)map->nx * sizeof(uint16_t), (size_t)map->nx * sizeof(uint16_t),
+            (size_t)map->ny, cudaMemcpyHostToDevice);
+}
+
+static size_t padded_nodes(const struct turtle_map * map, int * pitch)
+{
+        /* rows start on a 32-byte sector; one spare row keeps the +pitch gather
+         * of the closed upper edge inside the allocation */
+        *pitch = round_up(map->nx, 16);
+        return (size_t)*pitch * (size_t)(map->ny + 1);
+}
+
+extern "C" enum turtle_return turtle_stepper_freeze(
+    struct turtle_stepper * stepper, int device, struct turtle_plan ** plan_)
+{
+        *plan_ = NULL;
+        enum turtle_return rc = require_device(FN(&turtle_stepper_freeze), device);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        if (stepper->layers.empty() || stepper->layers[0].empty())
+                return tbh::raise(FN(&turtle_stepper_freeze), TURTLE_RETURN_DOMAIN_ERROR,
+                    BATCH_CU, __LINE__, "empty geometry");
+        rc = tbh::stepper_flatten(stepper, FN(&turtle_stepper_freeze));
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        const tb_flat_geometry & F = stepper->flat;
+
+        CUDA_TRY(&turtle_stepper_freeze, cudaSetDevice(device));
+        struct turtle_plan * plan = new (std::nothrow) turtle_plan();
+        if (plan == NULL)
+                return tbh::raise(FN(&turtle_stepper_freeze), TURTLE_RETURN_MEMORY_ERROR,
+                    BATCH_CU, __LINE__, "could not allocate memory");
+        memset(&plan->counters, 0x0, sizeof(plan->counters));
+        plan->device = device;
+        plan->pool = NULL;
+        plan->d_maps = NULL;
+        plan->d_tiles = NULL;
+        plan->d_counters = NULL;
+        plan->slot_rays = 0;
+        for (int s = 0; s < N_SLOTS; s++) {
+                plan->stream[s] = NULL;
+                plan->d_in[s] = NULL;
+                plan->d_out[s] = NULL;
+        }
+        cudaDeviceProp prop;
+        cudaGetDeviceProperties(&prop, device);
+        plan->sm_count = prop.multiProcessorCount;
+        plan->ctas_per_sm = 0;
+        plan->threads = 0;
+
+        /* residency plan: one pool for all grids, identical maps stored once */
+        const size_t n_maps = F.maps.size();
+        std::vector<size_t> offset(n_maps, 0);
+        std::vector<int> pitch(n_maps, 0);
+        std::map<const struct turtle_map *, size_t> first;
+        size_t total = 0;
+        for (size_t i = 0; i < n_maps; i++) {
+                std::map<const struct turtle_map *, size_t>::iterator it = first.find(F.src[i]);
+                if (it != first.end()) {
+                        offset[i] = offset[it->second];
+                        pitch[i] = pitch[it->second];
+                        continue;
+                }
+                first[F.src[i]] = i;
+                offset[i] = total;
+                total += (padded_nodes(F.src[i], &pitch[i]) + 127) / 128 * 128;
+        }
+        const size_t pool_bytes = std::max<size_t>(total, 128) * sizeof(uint16_t);
+        cudaError_t err = cudaMalloc(&plan->pool, pool_bytes);
+        if (err == cudaSuccess) err = cudaMemset(plan->pool, 0x0, pool_bytes);
+        std::vector<tb::MapDesc> maps = F.maps;
+        for (size_t i = 0; (i < n_maps) && (err == cudaSuccess); i++) {
+                uint16_t * dst = (uint16_t *)plan->pool + offset[i];
+                maps[i].nodes = dst;
+                maps[i].pitch = pitch[i];
+                if (first[F.src[i]] == i) err = upload_nodes(dst, pitch[i], F.src[i]);
+        }
+        const size_t maps_bytes = std::max<size_t>(n_maps, 1) * sizeof(tb::MapDesc);
+        const size_t tiles_bytes = std::max<size_t>(F.tiles.size(), 1) * sizeof(int);
+        if (err == cudaSuccess) err = cudaMalloc((void **)&plan->d_maps, maps_bytes);
+        if ((err == cudaSuccess) && n_maps)
+                err = cudaMemcpy(plan->d_maps, maps.data(), n_maps * sizeof(tb::MapDesc),
+                    cudaMemcpyHostToDevice);
+        if (err == cudaSuccess) err = cudaMalloc((void **)&plan->d_tiles, tiles_bytes);
+        if ((err == cudaSuccess) && !F.tiles.empty())
+                err = cudaMemcpy(plan->d_tiles, F.tiles.data(), F.tiles.size() * sizeof(int),
+                    cudaMemcpyHostToDevice);
+        if (err == cudaSuccess)
+                err = cudaMalloc((void **)&plan->d_counters,
+                    (N_SLOTS + 1) * 4 * sizeof(unsigned long long));
+        if (err != cudaSuccess) {
+                turtle_plan_destroy(&plan);
+                return tbh::raise(FN(&turtle_stepper_freeze), TURTLE_RETURN_LIBRARY_ERROR,
+                    BATCH_CU, __LINE__, "CUDA error while uploading the geometry: %s",
+                    cudaGetErrorString(err));
+        }
+        plan->G = F.G;
+        plan->G.maps = plan->d_maps;
+        plan->G.tiles = plan->d_tiles;
+        plan->bytes = pool_bytes + maps_bytes + tiles_bytes;
+        *plan_ = plan;
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" void turtle_plan_destroy(struct turtle_plan ** plan_)
+{
+        if ((plan_ == NULL) || (*plan_ == NULL)) return;
+        struct turtle_plan * plan = *plan_;
+        cudaSetDevice(plan->device);
+        for (int s = 0; s < N_SLOTS; s++) {
+                if (plan->stream[s] != NULL) {
+                        cudaStreamSynchronize(plan->stream[s]);
+                        cudaEventDestroy(plan->ev0[s]);
+                        cudaEventDestroy(plan->ev1[s]);
+                        cudaStreamDestroy(plan->stream[s]);
+                }
+                cudaFree(plan->d_in[s]);
+                cudaFree(plan->d_out[s]);
+        }
+        cudaFree(plan->pool);
+        cudaFree(plan->d_maps);
+        cudaFree(plan->d_tiles);
+        cudaFree(plan->d_counters);
+        delete plan;
+        *plan_ = NULL;
+}
+
+extern "C" int turtle_plan_device(const struct turtle_plan * plan) { return plan->device; }
+extern "C" size_t turtle_plan_bytes(const struct turtle_plan * plan) { return plan->bytes; }
+
+extern "C" void turtle_plan_counters_get(
+    const struct turtle_plan * plan, struct turtle_plan_counters * counters)
+{
+        *counters = plan->counters;
+}
+
+extern "C" void turtle_plan_launch_set(struct turtle_plan * plan, int ctas_per_sm, int threads)
+{
+        plan->ctas_per_sm = ctas_per_sm;
+        plan->threads = threads;
+}
+
+/* Grid of the persistent kernel: a multiple of the SM count. */
+static void trace_grid(const struct turtle_plan * plan, size_t n, int * blocks, int * threads)
+{
+        *threads = (plan->threads > 0) ? round_up(plan->threads, 32) : 128;
+        if (*threads > 128) *threads = 128; /* __launch_bounds__(128) */
+        const int per_sm = (plan->ctas_per_sm > 0) ? plan->ctas_per_sm : 4;
+        long long want = (long long)plan->sm_count * per_sm;
+        const long long need = (long long)((n + *threads - 1) / *threads);
+        if (need < want) want = (need > 0) ? need : 1;
+        *blocks = (int)want;
+}
+
+static enum turtle_return check_rule(turtle_function_t * fn, const struct turtle_trace_rule * rule)
+{
+        if ((rule == NULL) || !(rule->max_steps > 0) || isnan(rule->altitude_max) ||
+            isnan(rule->altitude_min) || isnan(rule->length_max))
+                return tbh::raise(fn, TURTLE_RETURN_DOMAIN_ERROR, BATCH_CU, __LINE__,
+                    "invalid trace rule");
+        return TURTLE_RETURN_SUCCESS;
+}
+
+static cudaError_t launch_trace(struct turtle_plan * plan, size_t n, const double * d_position,
+    const double * d_direction, const struct turtle_trace_rule * rule,
+    struct turtle_trace_result * d_results, unsigned long long * d_counters,
+    cudaStream_t stream)
+{
+        cudaError_t err = cudaMemsetAsync(d_counters, 0x0, 4 * sizeof(unsigned long long), stream);
+        if (err != cudaSuccess) return err;
+        TraceArgs A;
+        A.n = n;
+        A.position = d_position;
+        A.direction = d_direction;
+        A.results = d_results;
+        A.cursor = d_counters;
+        A.altitude_min = rule->altitude_min;
+        A.altitude_max = rule->altitude_max;
+        A.length_max = rule->length_max;
+        A.max_steps = rule->max_steps;
+        int blocks, threads;
+        trace_grid(plan, n, &blocks, &threads);
+        if (plan->G.range > 0.)
+                trace_kernel<true><<<blocks, threads, 0, stream>>>(plan->G, A);
+        else
+                trace_kernel<false><<<blocks, threads, 0, stream>>>(plan->G, A);
+        plan->counters.launches++;
+        return cudaGetLastError();
+}
+
+extern "C" enum turtle_return turtle_stepper_trace_batch_device(
+    struct turtle_plan * plan, size_t n, const double * position,
+    const double * direction, const struct turtle_trace_rule * rule,
+    struct turtle_trace_result * results, void * stream)
+{
+        enum turtle_return rc = check_rule(FN(&turtle_stepper_trace_batch_device), rule);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        if (n == 0) return TURTLE_RETURN_SUCCESS;
+        CUDA_TRY(&turtle_stepper_trace_batch_device, cudaSetDevice(plan->device));
+        memset(&plan->counters, 0x0, sizeof(plan->counters));
+        plan->counters.rays = n;
+        CUDA_TRY(&turtle_stepper_trace_batch_device,
+            launch_trace(plan, n, position, direction, rule, results,
+                plan->d_counters + 4 * N_SLOTS, (cudaStream_t)stream));
+        return TURTLE_RETURN_SUCCESS;
+}
+
+/* Lazily create the streams and staging buffers of the host-pointer pipeline. */
+static cudaError_t plan_pipeline(struct turtle_plan * plan, size_t rays)
+{
+        cudaError_t err = cudaSuccess;
+        for (int s = 0; (s < N_SLOTS) && (err == cudaSuccess); s++) {
+                if (plan->stream[s] == NULL) {
+                        err = cudaStreamCreateWithFlags(&plan->stream[s], cudaStreamNonBlocking);
+                        if (err == cudaSuccess) err = cudaEventCreate(&plan->ev0[s]);
+                        if (err == cudaSuccess) err = cudaEventCreate(&plan->ev1[s]);
+                }
+        }
+        if ((err == cudaSuccess) && (plan->slot_rays < rays)) {
+                for (int s = 0; s < N_SLOTS; s++) {
+                        cudaFree(plan->d_in[s]);
+                        cudaFree(plan->d_out[s]);
+                        plan->d_in[s] = NULL;
+                        plan->d_out[s] = NULL;
+                }
+                plan->slot_rays = 0;
+                for (int s = 0; (s < N_SLOTS) && (err == cudaSuccess); s++) {
+                        err = cudaMalloc((void **)&plan->d_in[s], rays * 6 * sizeof(double));
+                        if (err == cudaSuccess)
+                                err = cudaMalloc((void **)&plan->d_out[s],
+                                    rays * sizeof(turtle_trace_result));
+                }
+                if (err == cudaSuccess) plan->slot_rays = rays;
+        }
+        return err;
+}
+
+extern "C" void turtle_plan_counters_sync(struct turtle_plan * plan)
+{
+        /* device-pointer calls: the caller has synchronised its stream */
+        unsigned long long c[4];
+        cudaSetDevice(plan->device);
+        if (cudaMemcpy(c, plan->d_counters + 4 * N_SLOTS, sizeof c, cudaMemcpyDeviceToHost) ==
+            cudaSuccess) {
+                plan->counters.steps = c[1];
+                plan->counters.samples = c[2];
+        }
+}
+
+extern "C" enum turtle_return turtle_stepper_trace_batch(
+    struct turtle_plan * plan, size_t n, const double * position,
+    const double * direction, const struct turtle_trace_rule * rule,
+    struct turtle_trace_result * results)
+{
+        enum turtle_return rc = check_rule(FN(&turtle_stepper_trace_batch), rule);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        memset(&plan->counters, 0x0, sizeof(plan->counters));
+        if (n == 0) return TURTLE_RETURN_SUCCESS;
+        CUDA_TRY(&turtle_stepper_trace_batch, cudaSetDevice(plan->device));
+        const size_t chunk = std::min(n, CHUNK_RAYS);
+        CUDA_TRY(&turtle_stepper_trace_batch, plan_pipeline(plan, chunk));
+
+        /* chunked 3-deep pipeline: H2D(c+1) | kernel(c) | D2H(c-1) on 3 streams */
+        const size_t n_chunks = (n + chunk - 1) / chunk;
+        std::vector<unsigned long long> totals(4, 0ull);
+        double kernel_ms = 0.;
+        unsigned long long c4[4];
+        for (size_t c = 0; c < n_chunks + N_SLOTS; c++) {
+                const int s = (int)(c % N_SLOTS);
+                if (c >= N_SLOTS) { /* drain the slot before reusing it */
+                        CUDA_TRY(&turtle_stepper_trace_batch, cudaStreamSynchronize(plan->stream[s]));
+                        float ms = 0.f;
+                        cudaEventElapsedTime(&ms, plan->ev0[s], plan->ev1[s]);
+                        kernel_ms += ms;
+                        CUDA_TRY(&turtle_stepper_trace_batch,
+                            cudaMemcpy(c4, plan->d_counters + 4 * s, sizeof c4,
+                                cudaMemcpyDeviceToHost));
+                        totals[1] += c4[1];
+                        totals[2] += c4[2];
+                }
+                if (c >= n_chunks) continue;
+                const size_t i0 = c * chunk;
+                const size_t m = std::min(chunk, n - i0);
+                cudaStream_t st = plan->stream[s];
+                double * d_pos = plan->d_in[s];
+                double * d_dir = plan->d_in[s] + 3 * chunk;
+                CUDA_TRY(&turtle_stepper_trace_batch,
+                    cudaMemcpyAsync(d_pos, position + 3 * i0, m * 3 * sizeof(double),
+                        cudaMemcpyHostToDevice, st));
+                CUDA_TRY(&turtle_stepper_trace_batch,
+                    cudaMemcpyAsync(d_dir, direction + 3 * i0, m * 3 * sizeof(double),
+                        cudaMemcpyHostToDevice, st));
+                CUDA_TRY(&turtle_stepper_trace_batch, cudaEventRecord(plan->ev0[s], st));
+                CUDA_TRY(&turtle_stepper_trace_batch,
+                    launch_trace(plan, m, d_pos, d_dir, rule, plan->d_out[s],
+                        plan->d_counters + 4 * s, st));
+                CUDA_TRY(&turtle_stepper_trace_batch, cudaEventRecord(plan->ev1[s], st));
+                CUDA_TRY(&turtle_stepper_trace_batch,
+                    cudaMemcpyAsync(results + i0, plan->d_out[s],
+                        m * sizeof(turtle_trace_result), cudaMemcpyDeviceToHost, st));
+        }
+        plan->counters.rays = n;
+        plan->counters.steps = totals[1];
+        plan->counters.samples = totals[2];
+        plan->counters.kernel_ms = kernel_ms;
+        return TURTLE_RETURN_SUCCESS;
+}
+
+/* ---- particle states and single steps ----------------------------------------- */
+
+extern "C" enum turtle_return turtle_states_create(
+    struct turtle_plan * plan, size_t n, struct turtle_states ** states_)
+{
+        *states_ = NULL;
+        CUDA_TRY(&turtle_states_create, cudaSetDevice(plan->device));
+        struct turtle_states * states = new (std::nothrow) turtle_states();
+        if (states == NULL)
+                return tbh::raise(FN(&turtle_states_create), TURTLE_RETURN_MEMORY_ERROR,
+                    BATCH_CU, __LINE__, "could not allocate memory");
+        states->plan = plan;
+        states->n = n;
+        states->d_states = NULL;
+        cudaError_t err = cudaMalloc((void **)&states->d_states,
+            std::max<size_t>(n, 1) * sizeof(ParticleState));
+        if (err != cudaSuccess) {
+                delete states;
+                return tbh::raise(FN(&turtle_states_create), TURTLE_RETURN_MEMORY_ERROR,
+                    BATCH_CU, __LINE__, "could not allocate %zu particle states: %s", n,
+                    cudaGetErrorString(err));
+        }
+        *states_ = states;
+        return turtle_states_reset(states);
+}
+
+extern "C" void turtle_states_destroy(struct turtle_states ** states)
+{
+        if ((states == NULL) || (*states == NULL)) return;
+        cudaSetDevice((*states)->plan->device);
+        cudaFree((*states)->d_states);
+        delete *states;
+        *states = NULL;
+}
+
+extern "C" enum turtle_return turtle_states_reset(struct turtle_states * states)
+{
+        CUDA_TRY(&turtle_states_reset, cudaSetDevice(states->plan->device));
+        if (states->n == 0) return TURTLE_RETURN_SUCCESS;
+        const int blocks = (int)std::min<size_t>((states->n + 255) / 256,
+            (size_t)states->plan->sm_count * 8);
+        states_reset_kernel<<<blocks, 256>>>(states->d_states, states->n);
+        states->plan->counters.launches++;
+        CUDA_TRY(&turtle_states_reset, cudaGetLastError());
+        CUDA_TRY(&turtle_states_reset, cudaDeviceSynchronize());
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_stepper_step_batch_device(
+    struct turtle_plan * plan, struct turtle_states * states, size_t n,
+    double * position, const double * direction, double * latitude,
+    double * longitude, double * altitude, double * elevation, double * step,
+    int * index, void * stream)
+{
+        if ((states != NULL) && ((states->plan != plan) || (states->n < n)))
+                return tbh::raise(FN(&turtle_stepper_step_batch_device),
+                    TURTLE_RETURN_DOMAIN_ERROR, BATCH_CU, __LINE__,
+                    "states do not match the plan or are too few");
+        if (n == 0) return TURTLE_RETURN_SUCCESS;
+        CUDA_TRY(&turtle_stepper_step_batch_device, cudaSetDevice(plan->device));
+        StepArgs A;
+        A.n = n;
+        A.states = (states != NULL) ? states->d_states : NULL;
+        A.position = position;
+        A.direction = direction;
+        A.latitude = latitude;
+        A.longitude = longitude;
+        A.altitude = altitude;
+        A.elevation = elevation;
+        A.step = step;
+        A.index = index;
+        A.counters = plan->d_counters + 4 * N_SLOTS;
+        const int threads = 128;
+        const int blocks = (int)std::min<size_t>((n + threads - 1) / threads,
+            (size_t)plan->sm_count * 8);
+        if (plan->G.range > 0.)
+                step_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(plan->G, A);
+        else
+                step_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(plan->G, A);
+        plan->counters.launches++;
+        plan->counters.rays = n;
+        plan->counters.steps = (direction != NULL) ? n : 0;
+        CUDA_TRY(&turtle_stepper_step_batch_device, cudaGetLastError());
+        return TURTLE_RETURN_SUCCESS;
+}
+
+/* Small RAII helper for the host-pointer wrappers of the simple kernels. */
+namespace {
+struct DeviceBuffers {
+        std::vector<void *> ptrs;
+        ~DeviceBuffers()
+        {
+                for (size_t i = 0; i < ptrs.size(); i++) cudaFree(ptrs[i]);
+        }
+        /* allocate `bytes` and optionally copy from host; NULL host + copy_in=false = output */
+        cudaError_t get(void ** dev, const void * host, size_t bytes, bool copy_in)
+        {
+                *dev = NULL;
+                cudaError_t err = cudaMalloc(dev, std::max<size_t>(bytes, 8));
+                if (err != cudaSuccess) return err;
+                ptrs.push_back(*dev);
+                if (copy_in && (host != NULL) && bytes)
+                        err = cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice);
+                return err;
+        }
+};
+}
+
+#define DEV_IN(fn, B, dptr, hptr, bytes)                                           \
+        CUDA_TRY(fn, B.get((void **)&(dptr), (hptr), (bytes), true))
+#define DEV_OUT(fn, B, dptr, hptr, bytes)                                          \
+        do {                                                                       \
+                (dptr) = NULL;                                                     \
+                if ((hptr) != NULL)                                                \
+                        CUDA_TRY(fn, B.get((void **)&(dptr), NULL, (bytes), false)); \
+        } while (0)
+#define DEV_BACK(fn, hptr, dptr, bytes)                                            \
+        do {                                                                       \
+                if ((hptr) != NULL)                                                \
+                        CUDA_TRY(fn, cudaMemcpy((hptr), (dptr), (bytes),           \
+                                         cudaMemcpyDeviceToHost));                 \
+        } while (0)
+
+extern "C" enum turtle_return turtle_stepper_step_batch(struct turtle_plan * plan,
+    struct turtle_states * states, size_t n, double * position,
+    const double * direction, double * latitude, double * longitude,
+    double * altitude, double * elevation, double * step, int * index)
+{
+        if (n == 0) return TURTLE_RETURN_SUCCESS;
+        CUDA_TRY(&turtle_stepper_step_batch, cudaSetDevice(plan->device));
+        DeviceBuffers B;
+        double *d_pos, *d_dir = NULL, *d_lat, *d_lon, *d_alt, *d_el, *d_step;
+        int * d_idx;
+        DEV_IN(&turtle_stepper_step_batch, B, d_pos, position, n * 3 * sizeof(double));
+        if (direction != NULL)
+                DEV_IN(&turtle_stepper_step_batch, B, d_dir, direction, n * 3 * sizeof(double));
+        DEV_OUT(&turtle_stepper_step_batch, B, d_lat, latitude, n * sizeof(double));
+        DEV_OUT(&turtle_stepper_step_batch, B, d_lon, longitude, n * sizeof(double));
+        DEV_OUT(&turtle_stepper_step_batch, B, d_alt, altitude, n * sizeof(double));
+        DEV_OUT(&turtle_stepper_step_batch, B, d_el, elevation, n * 2 * sizeof(double));
+        DEV_OUT(&turtle_stepper_step_batch, B, d_step, step, n * sizeof(double));
+        DEV_OUT(&turtle_stepper_step_batch, B, d_idx, index, n * 2 * sizeof(int));
+        enum turtle_return rc = turtle_stepper_step_batch_device(plan, states, n, d_pos, d_dir,
+            d_lat, d_lon, d_alt, d_el, d_step, d_idx, NULL);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        CUDA_TRY(&turtle_stepper_step_batch, cudaDeviceSynchronize());
+        if (direction != NULL)
+                DEV_BACK(&turtle_stepper_step_batch, position, d_pos, n * 3 * sizeof(double));
+        DEV_BACK(&turtle_stepper_step_batch, latitude, d_lat, n * sizeof(double));
+        DEV_BACK(&turtle_stepper_step_batch, longitude, d_lon, n * sizeof(double));
+        DEV_BACK(&turtle_stepper_step_batch, altitude, d_alt, n * sizeof(double));
+        DEV_BACK(&turtle_stepper_step_batch, elevation, d_el, n * 2 * sizeof(double));
+        DEV_BACK(&turtle_stepper_step_batch, step, d_step, n * sizeof(double));
+        DEV_BACK(&turtle_stepper_step_batch, index, d_idx, n * 2 * sizeof(int));
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_stepper_position_batch(struct turtle_plan * plan,
+    size_t n, const double * latitude, const double * longitude, const double * height,
+    int layer_index, double * position, int * data_index)
+{
+        if ((layer_index < 0) || (layer_index >= plan->G.n_layers))
+                return tbh::raise(FN(&turtle_stepper_position_batch), TURTLE_RETURN_DOMAIN_ERROR,
+                    "src/turtle/stepper.c", __LINE__, "no valid data");
+        if (n == 0) return TURTLE_RETURN_SUCCESS;
+        CUDA_TRY(&turtle_stepper_position_batch, cudaSetDevice(plan->device));
+        DeviceBuffers B;
+        double *d_lat, *d_lon, *d_h, *d_pos;
+        int * d_idx;
+        DEV_IN(&turtle_stepper_position_batch, B, d_lat, latitude, n * sizeof(double));
+        DEV_IN(&turtle_stepper_position_batch, B, d_lon, longitude, n * sizeof(double));
+        DEV_IN(&turtle_stepper_position_batch, B, d_h, height, n * sizeof(double));
+        DEV_IN(&turtle_stepper_position_batch, B, d_pos, position, n * 3 * sizeof(double));
+        DEV_OUT(&turtle_stepper_position_batch, B, d_idx, data_index, n * sizeof(int));
+        const int blocks = (int)std::min<size_t>((n + 127) / 128, (size_t)plan->sm_count * 8);
+        position_kernel<<<blocks, 128>>>(plan->G, n, d_lat, d_lon, d_h, layer_index, d_pos, d_idx);
+        plan->counters.launches++;
+        CUDA_TRY(&turtle_stepper_position_batch, cudaGetLastError());
+        CUDA_TRY(&turtle_stepper_position_batch, cudaDeviceSynchronize());
+        DEV_BACK(&turtle_stepper_position_batch, position, d_pos, n * 3 * sizeof(double));
+        DEV_BACK(&turtle_stepper_position_batch, data_index, d_idx, n * sizeof(int));
+        return TURTLE_RETURN_SUCCESS;
+}
+
+/* ---- frame transforms ----------------------------------------------------------- */
+
+static int stream_blocks(size_t n, int threads)
+{
+        int device = 0, sms = 148;
+        cudaGetDevice(&device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        const size_t want = (n + threads - 1) / threads;
+        return (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)sms * 16));
+}
+
+static enum turtle_return require_current(turtle_function_t * fn)
+{
+        int device = 0;
+        if (turtle_b200_device_count() == 0)
+                return require_device(fn, 0);
+        cudaGetDevice(&device);
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_ecef_to_geodetic_batch_device(size_t n,
+    const double * ecef, double * latitude, double * longitude, double * altitude,
+    void * stream)
+{
+        enum turtle_return rc = require_current(FN(&turtle_ecef_to_geodetic_batch_device));
+        if ((rc != TURTLE_RETURN_SUCCESS) || (n == 0)) return rc;
+        to_geodetic_kernel<<<stream_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(
+            n, ecef, latitude, longitude, altitude);
+        CUDA_TRY(&turtle_ecef_to_geodetic_batch_device, cudaGetLastError());
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_ecef_to_geodetic_batch(size_t n, const double * ecef,
+    double * latitude, double * longitude, double * altitude)
+{
+        enum turtle_return rc = require_current(FN(&turtle_ecef_to_geodetic_batch));
+        if ((rc != TURTLE_RETURN_SUCCESS) || (n == 0)) return rc;
+        DeviceBuffers B;
+        double *d_ecef, *d_lat, *d_lon, *d_alt;
+        DEV_IN(&turtle_ecef_to_geodetic_batch, B, d_ecef, ecef, n * 3 * sizeof(double));
+        DEV_OUT(&turtle_ecef_to_geodetic_batch, B, d_lat, latitude, n * sizeof(double));
+        DEV_OUT(&turtle_ecef_to_geodetic_batch, B, d_lon, longitude, n * sizeof(double));
+        DEV_OUT(&turtle_ecef_to_geodetic_batch, B, d_alt, altitude, n * sizeof(double));
+        rc = turtle_ecef_to_geodetic_batch_device(n, d_ecef, d_lat, d_lon, d_alt, NULL);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        CUDA_TRY(&turtle_ecef_to_geodetic_batch, cudaDeviceSynchronize());
+        DEV_BACK(&turtle_ecef_to_geodetic_batch, latitude, d_lat, n * sizeof(double));
+        DEV_BACK(&turtle_ecef_to_geodetic_batch, longitude, d_lon, n * sizeof(double));
+        DEV_BACK(&turtle_ecef_to_geodetic_batch, altitude, d_alt, n * sizeof(double));
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_ecef_from_geodetic_batch_device(size_t n,
+    const double * latitude, const double * longitude, const double * elevation,
+    double * ecef, void * stream)
+{
+        enum turtle_return rc = require_current(FN(&turtle_ecef_from_geodetic_batch_device));
+        if ((rc != TURTLE_RETURN_SUCCESS) || (n == 0)) return rc;
+        from_geodetic_kernel<<<stream_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(
+            n, latitude, longitude, elevation, ecef);
+        CUDA_TRY(&turtle_ecef_from_geodetic_batch_device, cudaGetLastError());
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_ecef_from_geodetic_batch(size_t n,
+    const double * latitude, const double * longitude, const double * elevation,
+    double * ecef)
+{
+        enum turtle_return rc = require_current(FN(&turtle_ecef_from_geodetic_batch));
+        if ((rc != TURTLE_RETURN_SUCCESS) || (n == 0)) return rc;
+        DeviceBuffers B;
+        double *d_lat, *d_lon, *d_el, *d_ecef;
+        DEV_IN(&turtle_ecef_from_geodetic_batch, B, d_lat, latitude, n * sizeof(double));
+        DEV_IN(&turtle_ecef_from_geodetic_batch, B, d_lon, longitude, n * sizeof(double));
+        DEV_IN(&turtle_ecef_from_geodetic_batch, B, d_el, elevation, n * sizeof(double));
+        DEV_OUT(&turtle_ecef_from_geodetic_batch, B, d_ecef, ecef, n * 3 * sizeof(double));
+        rc = turtle_ecef_from_geodetic_batch_device(n, d_lat, d_lon, d_el, d_ecef, NULL);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        CUDA_TRY(&turtle_ecef_from_geodetic_batch, cudaDeviceSynchronize());
+        DEV_BACK(&turtle_ecef_from_geodetic_batch, ecef, d_ecef, n * 3 * sizeof(double));
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_ecef_from_horizontal_batch_device(size_t n,
+    const double * latitude, const double * longitude, const double * azimuth,
+    const double * elevation, double * direction, void * stream)
+{
+        enum turtle_return rc = require_current(FN(&turtle_ecef_from_horizontal_batch_device));
+        if ((rc != TURTLE_RETURN_SUCCESS) || (n == 0)) return rc;
+        from_horizontal_kernel<<<stream_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(
+            n, latitude, longitude, azimuth, elevation, direction);
+        CUDA_TRY(&turtle_ecef_from_horizontal_batch_device, cudaGetLastError());
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_ecef_from_horizontal_batch(size_t n,
+    const double * latitude, const double * longitude, const double * azimuth,
+    const double * elevation, double * direction)
+{
+        enum turtle_return rc = require_current(FN(&turtle_ecef_from_horizontal_batch));
+        if ((rc != TURTLE_RETURN_SUCCESS) || (n == 0)) return rc;
+        DeviceBuffers B;
+        double *d_lat, *d_lon, *d_az, *d_el, *d_dir;
+        DEV_IN(&turtle_ecef_from_horizontal_batch, B, d_lat, latitude, n * sizeof(double));
+        DEV_IN(&turtle_ecef_from_horizontal_batch, B, d_lon, longitude, n * sizeof(double));
+        DEV_IN(&turtle_ecef_from_horizontal_batch, B, d_az, azimuth, n * sizeof(double));
+        DEV_IN(&turtle_ecef_from_horizontal_batch, B, d_el, elevation, n * sizeof(double));
+        DEV_OUT(&turtle_ecef_from_horizontal_batch, B, d_dir, direction, n * 3 * sizeof(double));
+        rc = turtle_ecef_from_horizontal_batch_device(n, d_lat, d_lon, d_az, d_el, d_dir, NULL);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        CUDA_TRY(&turtle_ecef_from_horizontal_batch, cudaDeviceSynchronize());
+        DEV_BACK(&turtle_ecef_from_horizontal_batch, direction, d_dir, n * 3 * sizeof(double));
+        return TURTLE_RETURN_SUCCESS;
+}
+
+/* ---- map mirrors and elevation queries -------------------------------------------- */
+
+static std::mutex g_mirror_mutex;
+
+extern "C" void tb_map_release_mirrors(struct turtle_map * map)
+{
+        std::lock_guard<std::mutex> guard(g_mirror_mutex);
+        int current = 0;
+        bool have = !map->mirrors.empty() && (cudaGetDevice(&current) == cudaSuccess);
+        for (size_t i = 0; i < map->mirrors.size(); i++) {
+                if (map->mirrors[i].nodes == NULL) continue;
+                cudaSetDevice(map->mirrors[i].device);
+                cudaFree(map->mirrors[i].nodes);
+        }
+        if (have) cudaSetDevice(current);
+        map->mirrors.clear();
+}
+
+/* Device descriptor of `map` on the current device (uploads when stale). */
+static enum turtle_return map_mirror(turtle_function_t * fn, struct turtle_map * map,
+    tb::MapDesc * desc)
+{
+        enum turtle_return rc = require_current(fn);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        std::lock_guard<std::mutex> guard(g_mirror_mutex);
+        int device = 0;
+        CUDA_TRY(fn, cudaGetDevice(&device));
+        tb_device_mirror * mirror = NULL;
+        for (size_t i = 0; i < map->mirrors.size(); i++)
+                if (map->mirrors[i].device == device) mirror = &map->mirrors[i];
+        if (mirror == NULL) {
+                map->mirrors.push_back(tb_device_mirror());
+                mirror = &map->mirrors.back();
+                mirror->device = device;
+        }
+        if (mirror->nodes == NULL) {
+                const size_t count = padded_nodes(map, &mirror->pitch);
+                CUDA_TRY(fn, cudaMalloc((void **)&mirror->nodes, count * sizeof(uint16_t)));
+                CUDA_TRY(fn, cudaMemset(mirror->nodes, 0x0, count * sizeof(uint16_t)));
+                mirror->version = 0;
+        }
+        if (mirror->version != map->version) {
+                CUDA_TRY(fn, upload_nodes(mirror->nodes, mirror->pitch, map));
+                mirror->version = map->version;
+        }
+        desc->nodes = mirror->nodes;
+        desc->nx = map->nx;
+        desc->ny = map->ny;
+        desc->pitch = mirror->pitch;
+        desc->kind = map->kind;
+        desc->x0 = map->x0;
+        desc->y0 = map->y0;
+        desc->dx = map->dx;
+        desc->dy = map->dy;
+        desc->z0 = map->z0;
+        desc->dz = map->dz;
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_map_elevation_batch_device(struct turtle_map * map,
+    size_t n, const double * x, const double * y, double * z, int * inside, void * stream)
+{
+        tb::MapDesc M;
+        enum turtle_return rc = map_mirror(FN(&turtle_map_elevation_batch_device), map, &M);
+        if ((rc != TURTLE_RETURN_SUCCESS) || (n == 0)) return rc;
+        map_elevation_kernel<<<stream_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(
+            M, n, x, y, z, inside);
+        CUDA_TRY(&turtle_map_elevation_batch_device, cudaGetLastError());
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_map_elevation_batch(struct turtle_map * map, size_t n,
+    const double * x, const double * y, double * z, int * inside)
+{
+        enum turtle_return rc = require_current(FN(&turtle_map_elevation_batch));
+        if ((rc != TURTLE_RETURN_SUCCESS) || (n == 0)) return rc;
+        DeviceBuffers B;
+        double *d_x, *d_y, *d_z;
+        int * d_in;
+        DEV_IN(&turtle_map_elevation_batch, B, d_x, x, n * sizeof(double));
+        DEV_IN(&turtle_map_elevation_batch, B, d_y, y, n * sizeof(double));
+        DEV_IN(&turtle_map_elevation_batch, B, d_z, z, n * sizeof(double));
+        DEV_OUT(&turtle_map_elevation_batch, B, d_in, inside, n * sizeof(int));
+        rc = turtle_map_elevation_batch_device(map, n, d_x, d_y, d_z, d_in, NULL);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        CUDA_TRY(&turtle_map_elevation_batch, cudaDeviceSynchronize());
+        DEV_BACK(&turtle_map_elevation_batch, z, d_z, n * sizeof(double));
+        DEV_BACK(&turtle_map_elevation_batch, inside, d_in, n * sizeof(int));
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_map_elevation_ecef_batch_device(struct turtle_map * map,
+    size_t n, const double * ecef, double * latitude, double * longitude, double * altitude,
+    double * z, int * inside, void * stream)
+{
+        tb::MapDesc M;
+        enum turtle_return rc = map_mirror(FN(&turtle_map_elevation_ecef_batch_device), map, &M);
+        if ((rc != TURTLE_RETURN_SUCCESS) || (n == 0)) return rc;
+        tb::ProjDesc P;
+        tbh::projection_to_desc(turtle_map_projection(map), &P);
+        map_elevation_ecef_kernel<<<stream_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(
+            M, P, n, ecef, latitude, longitude, altitude, z, inside);
+        CUDA_TRY(&turtle_map_elevation_ecef_batch_device, cudaGetLastError());
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_map_elevation_ecef_batch(struct turtle_map * map, size_t n,
+    const double * ecef, double * latitude, double * longitude, double * altitude, double * z,
+    int * inside)
+{
+        enum turtle_return rc = require_current(FN(&turtle_map_elevation_ecef_batch));
+        if ((rc != TURTLE_RETURN_SUCCESS) || (n == 0)) return rc;
+        DeviceBuffers B;
+        double *d_ecef, *d_lat, *d_lon, *d_alt, *d_z;
+        int * d_in;
+        DEV_IN(&turtle_map_elevation_ecef_batch, B, d_ecef, ecef, n * 3 * sizeof(double));
+        DEV_OUT(&turtle_map_elevation_ecef_batch, B, d_lat, latitude, n * sizeof(double));
+        DEV_OUT(&turtle_map_elevation_ecef_batch, B, d_lon, longitude, n * sizeof(double));
+        DEV_OUT(&turtle_map_elevation_ecef_batch, B, d_alt, altitude, n * sizeof(double));
+        DEV_IN(&turtle_map_elevation_ecef_batch, B, d_z, z, n * sizeof(double));
+        DEV_OUT(&turtle_map_elevation_ecef_batch, B, d_in, inside, n * sizeof(int));
+        rc = turtle_map_elevation_ecef_batch_device(
+            map, n, d_ecef, d_lat, d_lon, d_alt, d_z, d_in, NULL);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        CUDA_TRY(&turtle_map_elevation_ecef_batch, cudaDeviceSynchronize());
+        DEV_BACK(&turtle_map_elevation_ecef_batch, latitude, d_lat, n * sizeof(double));
+        DEV_BACK(&turtle_map_elevation_ecef_batch, longitude, d_lon, n * sizeof(double));
+        DEV_BACK(&turtle_map_elevation_ecef_batch, altitude, d_alt, n * sizeof(double));
+        DEV_BACK(&turtle_map_elevation_ecef_batch, z, d_z, n * sizeof(double));
+        DEV_BACK(&turtle_map_elevation_ecef_batch, inside, d_in, n * sizeof(int));
+        return TURTLE_RETURN_SUCCESS;
+}
+
+/* ---- FP64 peak ------------------------------------------------------------------------ */
+
+extern "C" double turtle_b200_dfma_peak(int repeats)
+{
+        if (turtle_b200_device_count() == 0) return 0.;
+        int device = 0, sms = 148;
+        cudaGetDevice(&device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        const int blocks = sms * 8, threads = 256, iterations = 1 << 14;
+        double * out = NULL;
+        if (cudaMalloc((void **)&out, (size_t)blocks * threads * sizeof(double)) != cudaSuccess)
+                return 0.;
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        double best = 0.;
+        if (repeats < 1) repeats = 1;
+        for (int r = 0; r < repeats + 1; r++) {
+                cudaEventRecord(e0);
+                dfma_kernel<<<blocks, threads>>>(out, iterations);
+                cudaEventRecord(e1);
+                cudaEventSynchronize(e1);
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e0, e1);
+                const double gops = (double)blocks * threads * 8. * iterations / (ms * 1e6);
+                if ((r > 0) && (gops > best)) best = gops; /* r = 0 is the warm-up */
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cudaFree(out);
+        return best;
+}
+
+/* Names of the batched entry points, for the error message format. */
+extern "C" const char * tb_batch_function_name(turtle_function_t * caller)
+{
+#define NAME(function) \
+        if (caller == (turtle_function_t *)function) return #function
+        NAME(turtle_stepper_freeze);
+        NAME(turtle_stepper_trace_batch);
+        NAME(turtle_stepper_trace_batch_device);
+        NAME(turtle_stepper_step_batch);
+        NAME(turtle_stepper_step_batch_device);
+        NAME(turtle_stepper_position_batch);
+        NAME(turtle_states_create);
+        NAME(turtle_states_reset);
+        NAME(turtle_ecef_to_geodetic_batch);
+        NAME(turtle_ecef_to_geodetic_batch_device);
+        NAME(turtle_ecef_from_geodetic_batch);
+        NAME(turtle_ecef_from_geodetic_batch_device);
+        NAME(turtle_ecef_from_horizontal_batch);
+        NAME(turtle_ecef_from_horizontal_batch_device);
+        NAME(turtle_map_elevation_batch);
+        NAME(turtle_map_elevation_batch_device);
+        NAME(turtle_map_elevation_ecef_batch);
+        NAME(turtle_map_elevation_ecef_batch_device);
+#undef NAME
+        return NULL;
+}
