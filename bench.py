@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- Mrays/s of the batched DEM ray stepper on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "C2"): a muography fan of
+4096 x 4096 = 16 Mi rays from a detector at (46.5 N, 3.5 E) + 1 m through a synthetic
+SRTMGL1-shaped 3 x 3 stack of 3601 x 3601 one-arc-second tiles, geodetic coordinates,
+range 0 (no local approximation), slope 0.4, resolution 1e-2. A ray stops when it
+leaves the stack (index[0] < 0), rises above 9000 m or after 1e5 steps.
+
+One "step" of this bench = one pass of the hot path over the whole batch of rays of
+every rank. Scaling is weak: each rank (one per GPU, DEM replicated) traces its own
+16 Mi-ray fan (rank r looks from a detector shifted by r * 0.01 degrees); rank 0 then
+gathers the 96-byte result records of all ranks over NCCL, inside the timed region.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--rays R] [--impl reference]
+
+prints ONE JSON line (see the keys at the bottom of main()).
+  value      whole-job Mrays/s with rays resident in HBM (device-pointer C ABI call)
+  e2e        the same through turtle_stepper_trace_batch with pinned HOST buffers,
+             host<->device copies inside the timed region
+  roofline   the trace kernel against the measured FP64 FMA peak of this GPU (the
+             path is FP64-pipe / issue bound, not HBM bound: DESIGN.md) -- plus the
+             HBM side for reference
+  cpu_baseline  the reference's own CPU stepper (oracle/_ref, else the C port) on all
+             host cores, on a strided sample of the same rays
+`--impl reference` times that CPU path alone, same metric / unit / config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DET_LAT, DET_LON, DET_HEIGHT = 46.5, 3.5, 1.0
+STACK_LAT0, STACK_LON0, STACK_N = 45, 2, 3
+ALTITUDE_MAX, MAX_STEPS = 9000.0, 100000
+N_AZ = N_EL = 4096
+OPS_PER_SAMPLE = 480.0   # FP64 pipe instructions per geodetic-stack sample
+BYTES_PER_RAY = 48 + 96  # position + direction in, result record out
+BYTES_PER_SAMPLE = 8     # four 16-bit nodes
+
+
+def stack_dir():
+    return os.environ.get("TURTLE_BENCH_STACK", "/tmp/turtle_b200_stack3601")
+
+
+def make_stack():
+    from turtle_b200 import synth
+    return synth.write_hgt_stack(stack_dir(), STACK_LAT0, STACK_LON0, STACK_N, STACK_N, n=3601)
+
+
+def fan(rank, first, count, n_az=N_AZ, n_el=N_EL):
+    """Directions of rays [first, first + count) of the fan of `rank`."""
+    from turtle_b200 import synth
+    lat, lon = DET_LAT + 0.01 * rank, DET_LON + 0.01 * rank
+    return lat, lon, synth.fan_directions(lat, lon, n_az, n_el, first=first, count=count)
+
+
+def fan_subsample(rank, stride, n_total):
+    """Every `stride`-th ray of the fan (ray index order preserved)."""
+    from turtle_b200 import synth
+    lat, lon = DET_LAT + 0.01 * rank, DET_LON + 0.01 * rank
+    r = np.arange(0, n_total, stride, dtype=np.int64)
+    i, j = r // N_EL, r % N_EL
+    az = 360.0 * (i + 0.5) / N_AZ
+    el = 0.5 + 29.5 * (j + 0.5) / N_EL
+    return synth.np_from_horizontal(np.full(len(r), lat), np.full(len(r), lon), az, el)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2 and len(r) >= 7] or \
+               [r for (_, r) in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower() == "active" for r in rows)]
+        power = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]),
+                "power_w_max": max(power) if power else None, "samples": len(rows),
+                "reasons": reasons}
+
+
+def reference_driver():
+    """The reference CPU stepper (oracle/_ref when it was compiled, else the C port)
+    behind the pthread ray loop of oracle/trace_driver.c, on the bench geometry."""
+    from oracle import harness as H
+    lib = H.best_oracle()
+    d = H.Driver(lib)
+    st = d.stack_create(stack_dir(), locked=True)  # mutex lock => one client per thread
+    d.geometry([(H.ADD_STACK, st, 0.)], range=0., slope=0.4, resolution=1e-2)
+    kind = "reference" if lib == H.REF else "port"
+    return d, H, kind
+
+
+def cpu_trace(d, H, rank, stride, n_total, cores):
+    lat, lon = DET_LAT + 0.01 * rank, DET_LON + 0.01 * rank
+    pos, _ = d.position([lat], [lon], [DET_HEIGHT], 0)
+    dirs = fan_subsample(rank, stride, n_total)
+    res, steps, seconds = d.trace(np.repeat(pos, len(dirs), 0), dirs,
+                                  H.rule(ALTITUDE_MAX, max_steps=MAX_STEPS), threads=cores)
+    return res, steps, seconds, len(dirs)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path, all host cores, bounded sample/step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    make_stack()
+    d, H, kind = reference_driver()
+    cores = os.cpu_count() or 1
+    n_total = args.rays
+    stride = max(1, n_total // args.ref_rays)
+    for _ in range(max(args.warmup, 0)):
+        cpu_trace(d, H, 0, stride * 8, n_total, cores)
+    t_all, rays_all, steps_all = 0., 0, 0
+    for _ in range(args.steps):
+        _, steps, seconds, n = cpu_trace(d, H, 0, stride, n_total, cores)
+        t_all += seconds
+        rays_all += n
+        steps_all += steps
+    value = rays_all / t_all / 1e6
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "ns_per_step": 1e9 * t_all / max(steps_all, 1),
+        "config": workload_config(n_total, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind,
+                         "sample": "every %d-th ray of the fan (%d rays per step), "
+                                   "one stepper + client per pthread" % (stride, rays_all // args.steps)},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n_rays, gpus):
+    return {"workload": "C2: %d-ray muography fan per GPU (4096 az x 4096 el, el 0.5-30 deg) from "
+                        "(46.5N, 3.5E)+1 m through a synthetic SRTMGL1-shaped 3x3 stack of "
+                        "3601x3601 int16 tiles (233 MB), geodetic, range 0, slope 0.4, "
+                        "resolution 1e-2; stop: leaves stack | alt > 9000 m | 1e5 steps" % n_rays,
+            "rays_per_gpu": n_rays, "parallelism": "rays sharded x%d, DEM replicated" % gpus,
+            "l2": "inputs + outputs per step (%.0f MB per GPU) exceed the 126 MB L2; "
+                  "no explicit flush" % (n_rays * BYTES_PER_RAY / 1e6)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--rays", type=int, default=N_AZ * N_EL, help="rays per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-rays", type=int, default=1 << 20,
+                    help="rays per step of the --impl reference arm")
+    ap.add_argument("--cpu-rays", type=int, default=1 << 22,
+                    help="rays of the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import turtle_b200 as tb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if tb.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: turtle_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- geometry: rank 0 writes the tiles once, every rank freezes its own copy ------
+    if rank == 0:
+        make_stack()
+    if world > 1:
+        dist.barrier()
+    stack = tb.Stack(stack_dir())
+    stepper = tb.Stepper(range=0., slope=0.4, resolution=1e-2)
+    stepper.add_stack(stack, 0.)
+    plan = stepper.freeze(local)
+    plan.launch_set(args.ctas_per_sm, args.threads)
+    rule = tb.trace_rule(ALTITUDE_MAX, max_steps=MAX_STEPS)
+
+    # ---- rays of this rank (pinned host copies for the e2e leg) -------------------------
+    n = args.rays
+    lat, lon, dirs = fan(rank, 0, n) if n == N_AZ * N_EL else (
+        DET_LAT + 0.01 * rank, DET_LON + 0.01 * rank,
+        fan_subsample(rank, (N_AZ * N_EL) // n, N_AZ * N_EL)[:n])
+    origin, data_index = stepper.position(lat, lon, DET_HEIGHT, 0)
+    assert data_index == 0
+    h_pos = torch.empty((n, 3), dtype=torch.float64, pin_memory=True)
+    h_dir = torch.empty((n, 3), dtype=torch.float64, pin_memory=True)
+    h_pos.numpy()[:] = origin[None, :]
+    h_dir.numpy()[:] = dirs
+    del dirs
+    h_res = torch.empty((n, 96), dtype=torch.uint8, pin_memory=True)
+    d_pos = h_pos.to(dev)
+    d_dir = h_dir.to(dev)
+    d_res = torch.empty((n, 96), dtype=torch.uint8, device=dev)
+    gathered = torch.empty((world, n, 96), dtype=torch.uint8, device=dev) \
+        if (world > 1 and rank == 0) else None
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        plan.trace_device(n, d_pos, d_dir, rule, d_res, stream=stream.cuda_stream)
+        if world > 1:  # the only exchange of the path: gather the records on rank 0
+            dist.gather(d_res, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
+
+    def timed(fn, steps):
+        """EXACTLY `steps` calls bracketed by barrier + synchronize, max over ranks."""
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t1 = time.time()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), t0, t1
+
+    # ---- device-resident throughput ------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total, t0, t1 = timed(step_device, args.steps)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    counters = plan.counters(sync=True)  # of the last launch
+    launches = args.steps
+    ms_step = ms_total / args.steps
+    value = world * n / (ms_step * 1e-3) / 1e6
+
+    # kernel alone (no gather), CUDA events on the launching stream: the roofline input
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    k0.record(stream)
+    for _ in range(args.steps):
+        plan.trace_device(n, d_pos, d_dir, rule, d_res, stream=stream.cuda_stream)
+    k1.record(stream)
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / args.steps
+    launches += args.steps
+
+    # ---- end to end through the host-pointer C ABI call -------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        res_np = h_res.numpy().view(tb.TRACE_RESULT).reshape(n)
+
+        def step_host():
+            plan.trace(h_pos.numpy(), h_dir.numpy(), rule, results=res_np)
+        step_host()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        w = torch.tensor([time.perf_counter() - w0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(w, op=dist.ReduceOp.MAX)
+        launches += plan.counters()["launches"] * args.steps
+        e2e = {"value": world * n * args.steps / float(w.item()) / 1e6, "unit": "Mrays/s",
+               "h2d_bytes_per_step": int(n * 48), "d2h_bytes_per_step": int(n * 96),
+               "ms_per_step": 1e3 * float(w.item()) / args.steps,
+               "api": "turtle_stepper_trace_batch (pinned host buffers, 3-deep chunk pipeline)"}
+        # the two paths must agree bit for bit
+        same = bool((torch.from_numpy(h_res.numpy()) == d_res.cpu()).all())
+        e2e["matches_device_path"] = same
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak, hbm_src = 6650.0, "fallback"
+    if os.path.exists(peaks_path):
+        hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
+    dfma = tb.dfma_peak(3)  # G FP64-pipe instructions / s, measured now on this GPU
+    samples, steps = counters["samples"], counters["steps"]
+    achieved_ops = OPS_PER_SAMPLE * samples / (kernel_ms * 1e-3) / 1e12
+    alg_bytes = n * BYTES_PER_RAY + samples * BYTES_PER_SAMPLE
+    roofline = {
+        "kernel": "trace_kernel<false>", "bound": "fp64",
+        "achieved": achieved_ops, "peak": dfma / 1e3, "unit": "Tinst/s (FP64 pipe; FMA = 1)",
+        "frac": achieved_ops / (dfma / 1e3) if dfma > 0 else None,
+        "peak_source": "turtle_b200_dfma_peak() measured in this run (MEASURED_PEAKS.json has "
+                       "no FP64 entry)",
+        "ops_per_sample": OPS_PER_SAMPLE, "samples_per_launch": samples,
+        "kernel_ms": kernel_ms, "traffic": None,
+        "hbm": {"achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                "unit": "GB/s", "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                "algorithmic_bytes": alg_bytes, "peak_source": hbm_src},
+    }
+
+    # ---- the reference's CPU path on this box, bounded sample ------------------------------------
+    cpu = None
+    if args.cpu_rays > 0:
+        d, H, kind = reference_driver()
+        cores = os.cpu_count() or 1
+        stride = max(1, (N_AZ * N_EL) // args.cpu_rays)
+        ref, ref_steps, seconds, m = cpu_trace(d, H, 0, stride, N_AZ * N_EL, cores)
+        cpu = {"value": m / seconds / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
+               "ns_per_step": 1e9 * seconds / max(ref_steps, 1), "seconds": seconds,
+               "sample": "every %d-th ray of the rank-0 fan (%d rays)" % (stride, m)}
+        if n == N_AZ * N_EL:  # parity of the same rays, for the record
+            got = d_res.cpu().numpy().view(tb.TRACE_RESULT).reshape(n)[::stride]
+            disc = ((got["n_steps"] != ref["n_steps"]) | (got["status"] != ref["status"]) |
+                    (got["medium_hash"] != ref["medium_hash"]) |
+                    (got["index"] != ref["index"]).any(1))
+            ok = ~disc
+            rock = np.abs(got["length"][:, 0] - ref["length"][:, 0])
+            cpu["parity"] = {"rays": int(m), "discrete_mismatch": int(disc.sum()),
+                             "rock_length_max_abs_diff_m": float(rock[ok].max()),
+                             "rock_length_over_1mm": int((rock[ok] > 1e-3).sum())}
+
+    line = {
+        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(n, world),
+        "ns_per_step": kernel_ms * 1e6 / max(steps, 1),
+        "steps_per_ray": steps / n, "samples_per_step": samples / max(steps, 1),
+        "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,
+        "cpu_baseline": cpu, "plan_bytes": plan.bytes,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -103,6 +103,7 @@ class Driver:
         self.d = _load_driver()
         self.library = library
         self.h = self.d.td_open(library.encode())
+        self._unlocked_stacks = 0
         if not self.h:
             raise OSError("could not open %s" % library)
 
@@ -129,6 +130,7 @@ class Driver:
 
     def stack_create(self, path, locked=False):
         i = self.d.td_stack_create(self.h, path.encode(), int(locked))
+        self._unlocked_stacks += 0 if locked else 1
         if i < 0:
             raise RuntimeError("stack_create failed: %s" % self.d.td_last_error(self.h).decode())
         return i
@@ -143,6 +145,10 @@ class Driver:
     def trace(self, position, direction, rule_, threads=1):
         position, direction = _f8(position, (-1, 3)), _f8(direction, (-1, 3))
         n = len(position)
+        if threads > 1 and self._unlocked_stacks:
+            # the reference's stack mutates its MRU list on every lookup (stack.c:325):
+            # threads need a locked stack (=> one client per stepper)
+            raise ValueError("multi-threaded tracing needs stack_create(..., locked=True)")
         out = np.zeros(n, dtype=RESULT)
         seconds = C.c_double()
         steps = self.d.td_trace(self.h, n, _p(position), _p(direction), C.byref(rule_), _p(out),
@@ -157,6 +163,8 @@ class Driver:
         position = _f8(position, (-1, 3)).copy()
         direction = _f8(direction)
         n_steps, n = direction.shape[0], direction.shape[1]
+        if threads > 1 and self._unlocked_stacks:
+            raise ValueError("multi-threaded walks need stack_create(..., locked=True)")
         step = np.empty((n_steps, n))
         altitude = np.empty((n_steps, n))
         index = np.empty((n_steps, n, 2), dtype=np.int32)

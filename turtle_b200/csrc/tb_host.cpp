@@ -22,6 +22,7 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <mutex>
 #include <new>
 
 #define FN(f) ((turtle_function_t *)(f))
@@ -1040,9 +1041,12 @@ extern "C" enum turtle_return turtle_stepper_create(struct turtle_stepper ** ste
         return TURTLE_RETURN_SUCCESS;
 }
 
+static std::mutex g_residency_mutex;
+
 /* Drop the cached flattening (and the tile pins it holds) before any change. */
 static void stepper_invalidate(struct turtle_stepper * s)
 {
+        std::lock_guard<std::mutex> guard(g_residency_mutex);
         if (!s->dirty)
                 for (size_t i = 0; i < s->data.size(); i++)
                         if ((s->data[i].kind == tb::DATA_STACK) &&
@@ -1212,6 +1216,9 @@ extern "C" enum turtle_return turtle_stepper_add_flat(
         return TURTLE_RETURN_SUCCESS;
 }
 
+/* Steppers of different threads may share maps and stacks (one stepper per thread
+ * is the reference's threading model, turtle.h:141-149): residency changes of a
+ * stack are serialised here. */
 /* Flatten the lists into tb::Geometry (host pointers). */
 enum turtle_return tbh::stepper_flatten(struct turtle_stepper * s,
     turtle_function_t * caller)
@@ -1222,6 +1229,7 @@ enum turtle_return tbh::stepper_flatten(struct turtle_stepper * s,
                 s->flat.G.resolution = s->resolution_factor;
                 return TURTLE_RETURN_SUCCESS;
         }
+        std::lock_guard<std::mutex> guard(g_residency_mutex);
         tb_flat_geometry & F = s->flat;
         F.maps.clear();
         F.src.clear();
