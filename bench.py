@@ -2,7 +2,8 @@
 """bench.py -- Mrays/s of the batched DEM ray stepper on B200 (BASELINE.json metric).
 
 Workload (BASELINE.json configs[1], SURVEY.md section 8d "C2"): a muography fan of
-4096 x 4096 = 16 Mi rays from a detector at (46.5 N, 3.5 E) + 1 m through a synthetic
+4096 x 4096 = 16 Mi rays (elevation-major order, lowest elevation first:
+turtle_b200.synth.fan_angles) from a detector at (46.5 N, 3.5 E) + 1 m through a synthetic
 SRTMGL1-shaped 3 x 3 stack of 3601 x 3601 one-arc-second tiles, geodetic coordinates,
 range 0 (no local approximation), slope 0.4, resolution 1e-2. A ray stops when it
 leaves the stack (index[0] < 0), rises above 9000 m or after 1e5 steps.
@@ -42,7 +43,10 @@ DET_LAT, DET_LON, DET_HEIGHT = 46.5, 3.5, 1.0
 STACK_LAT0, STACK_LON0, STACK_N = 45, 2, 3
 ALTITUDE_MAX, MAX_STEPS = 9000.0, 100000
 N_AZ = N_EL = 4096
-OPS_PER_SAMPLE = 480.0   # FP64 pipe instructions per geodetic-stack sample
+# FP64-pipe instructions (DFMA/DMUL/DADD/DSETP, FMA = 1) per geodetic-stack sample: 382
+# measured with ncu (profiles/r01_trace_kernel_ncu_full.md: sm__inst_executed_pipe_fp64 /
+# samples); the static estimate of SURVEY.md App. C is 480 (it counts both branches).
+OPS_PER_SAMPLE = 382.0
 BYTES_PER_RAY = 48 + 96  # position + direction in, result record out
 BYTES_PER_SAMPLE = 8     # four 16-bit nodes
 
@@ -68,9 +72,7 @@ def fan_subsample(rank, stride, n_total):
     from turtle_b200 import synth
     lat, lon = DET_LAT + 0.01 * rank, DET_LON + 0.01 * rank
     r = np.arange(0, n_total, stride, dtype=np.int64)
-    i, j = r // N_EL, r % N_EL
-    az = 360.0 * (i + 0.5) / N_AZ
-    el = 0.5 + 29.5 * (j + 0.5) / N_EL
+    az, el = synth.fan_angles(r, N_AZ, N_EL)
     return synth.np_from_horizontal(np.full(len(r), lat), np.full(len(r), lon), az, el)
 
 
@@ -173,7 +175,8 @@ def run_reference(args):
 
 
 def workload_config(n_rays, gpus):
-    return {"workload": "C2: %d-ray muography fan per GPU (4096 az x 4096 el, el 0.5-30 deg) from "
+    return {"workload": "C2: %d-ray muography fan per GPU (4096 az x 4096 el, el 0.5-30 deg, "
+                        "elevation-major ray order) from "
                         "(46.5N, 3.5E)+1 m through a synthetic SRTMGL1-shaped 3x3 stack of "
                         "3601x3601 int16 tiles (233 MB), geodetic, range 0, slope 0.4, "
                         "resolution 1e-2; stop: leaves stack | alt > 9000 m | 1e5 steps" % n_rays,
@@ -246,14 +249,14 @@ def main():
     d_pos = h_pos.to(dev)
     d_dir = h_dir.to(dev)
     d_res = torch.empty((n, 96), dtype=torch.uint8, device=dev)
-    gathered = torch.empty((world, n, 96), dtype=torch.uint8, device=dev) \
+    gathered = [torch.empty((n, 96), dtype=torch.uint8, device=dev) for _ in range(world)] \
         if (world > 1 and rank == 0) else None
     stream = torch.cuda.current_stream()
 
     def step_device():
         plan.trace_device(n, d_pos, d_dir, rule, d_res, stream=stream.cuda_stream)
         if world > 1:  # the only exchange of the path: gather the records on rank 0
-            dist.gather(d_res, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
+            dist.gather(d_res, gathered, dst=0)
 
     def timed(fn, steps):
         """EXACTLY `steps` calls bracketed by barrier + synchronize, max over ranks."""
@@ -315,10 +318,12 @@ def main():
         w = torch.tensor([time.perf_counter() - w0], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(w, op=dist.ReduceOp.MAX)
-        launches += plan.counters()["launches"] * args.steps
+        hc = plan.counters()
+        launches += hc["launches"] * args.steps
         e2e = {"value": world * n * args.steps / float(w.item()) / 1e6, "unit": "Mrays/s",
                "h2d_bytes_per_step": int(n * 48), "d2h_bytes_per_step": int(n * 96),
                "ms_per_step": 1e3 * float(w.item()) / args.steps,
+               "kernel_ms_sum_per_step": hc["kernel_ms"], "chunks_per_step": hc["launches"],
                "api": "turtle_stepper_trace_batch (pinned host buffers, 3-deep chunk pipeline)"}
         # the two paths must agree bit for bit
         same = bool((torch.from_numpy(h_res.numpy()) == d_res.cpu()).all())

@@ -69,9 +69,10 @@ __device__ __forceinline__ bool finite3(const double v[3])
         return isfinite(v[0]) && isfinite(v[1]) && isfinite(v[2]);
 }
 
-/* The persistent ray-tracing kernel. */
-template <bool LLA>
-__global__ void __launch_bounds__(128)
+/* The persistent ray-tracing kernel. MINB = CTAs of 128 threads per SM the register
+ * allocation is bounded for (occupancy vs spills is a measured trade). */
+template <bool LLA, int MINB>
+__global__ void __launch_bounds__(128, MINB)
     trace_kernel(const __grid_constant__ tb::Geometry G, const TraceArgs A)
 {
         const unsigned lane = threadIdx.x & 31u;
@@ -708,15 +709,16 @@ extern "C" void turtle_plan_launch_set(struct turtle_plan * plan, int ctas_per_s
 }
 
 /* Grid of the persistent kernel: a multiple of the SM count. */
-static void trace_grid(const struct turtle_plan * plan, size_t n, int * blocks, int * threads)
+static int trace_grid(const struct turtle_plan * plan, size_t n, int * blocks, int * threads)
 {
         *threads = (plan->threads > 0) ? round_up(plan->threads, 32) : 128;
-        if (*threads > 128) *threads = 128; /* __launch_bounds__(128) */
+        if (*threads > 128) *threads = 128; /* __launch_bounds__(128, .) */
         const int per_sm = (plan->ctas_per_sm > 0) ? plan->ctas_per_sm : 4;
         long long want = (long long)plan->sm_count * per_sm;
         const long long need = (long long)((n + *threads - 1) / *threads);
         if (need < want) want = (need > 0) ? need : 1;
         *blocks = (int)want;
+        return per_sm;
 }
 
 static enum turtle_return check_rule(turtle_function_t * fn, const struct turtle_trace_rule * rule)
@@ -746,11 +748,28 @@ static cudaError_t launch_trace(struct turtle_plan * plan, size_t n, const doubl
         A.length_max = rule->length_max;
         A.max_steps = rule->max_steps;
         int blocks, threads;
-        trace_grid(plan, n, &blocks, &threads);
-        if (plan->G.range > 0.)
-                trace_kernel<true><<<blocks, threads, 0, stream>>>(plan->G, A);
+        const int per_sm = trace_grid(plan, n, &blocks, &threads);
+        const bool lla = plan->G.range > 0.;
+#define TRACE_LAUNCH(MINB)                                                             \
+        do {                                                                           \
+                if (lla)                                                               \
+                        trace_kernel<true, MINB><<<blocks, threads, 0, stream>>>(plan->G, A);  \
+                else                                                                   \
+                        trace_kernel<false, MINB><<<blocks, threads, 0, stream>>>(plan->G, A); \
+        } while (0)
+        /* the register budget follows the requested residency (in units of 128 threads) */
+        const int minb = per_sm * threads / 128;
+        if (minb <= 3)
+                TRACE_LAUNCH(3);
+        else if (minb == 4)
+                TRACE_LAUNCH(4);
+        else if (minb == 5)
+                TRACE_LAUNCH(5);
+        else if (minb <= 7)
+                TRACE_LAUNCH(6);
         else
-                trace_kernel<false><<<blocks, threads, 0, stream>>>(plan->G, A);
+                TRACE_LAUNCH(8);
+#undef TRACE_LAUNCH
         plan->counters.launches++;
         return cudaGetLastError();
 }
