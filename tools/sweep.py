@@ -26,7 +26,7 @@ def main():
     d_pos, d_dir = h_pos.cuda(), h_dir.cuda()
     d_res = torch.empty((n, 96), dtype=torch.uint8, device="cuda")
     res_np = h_res.numpy().view(tb.TRACE_RESULT).reshape(n)
-    configs = [(4, 128), (3, 128), (5, 128), (6, 128), (8, 128), (16, 32), (20, 32), (24, 32), (8, 64), (12, 64)]
+    configs = [(4, 128), (5, 128), (6, 128), (8, 128), (16, 32), (24, 32), (32, 32)]
     for (c, t) in configs:
         plan.launch_set(c, t)
         for _ in range(2):

@@ -350,6 +350,8 @@ static tb::MapDesc map_desc(const struct turtle_map * map)
         d.dy = map->dy;
         d.z0 = map->z0;
         d.dz = map->dz;
+        d.nx1 = (double)(map->nx - 1);
+        d.ny1 = (double)(map->ny - 1);
         return d;
 }
 
@@ -900,6 +902,7 @@ static enum turtle_return stack_elevation_scalar(struct turtle_stack * stack,
                                 hgt_parse_name(stack->path[cell].c_str(), &nxy, &x0, &y0);
                                 tb::MapDesc d;
                                 d.nx = d.ny = nxy;
+                                d.nx1 = d.ny1 = (double)(nxy - 1);
                                 d.x0 = x0;
                                 d.y0 = y0;
                                 d.dx = d.dy = 1. / (nxy - 1);
@@ -1286,19 +1289,47 @@ enum turtle_return tbh::stepper_flatten(struct turtle_stepper * s,
                         S.nlat = st->latitude_n;
                         S.nlon = st->longitude_n;
                         S.tile0 = (int)F.tiles.size();
+                        const tb::TileRec none = { NULL, 0., 0., -1, 0 };
+                        const struct turtle_map * first = NULL;
+                        S.uniform = 1;
                         for (size_t c = 0; c < st->tile.size(); c++) {
-                                if (st->tile[c] == NULL) {
-                                        F.tiles.push_back(-1);
-                                } else {
-                                        F.tiles.push_back((int)F.maps.size());
-                                        F.maps.push_back(map_desc(st->tile[c]));
-                                        F.src.push_back(st->tile[c]);
+                                const struct turtle_map * t = st->tile[c];
+                                if (t == NULL) {
+                                        F.tiles.push_back(none);
+                                        continue;
                                 }
+                                const tb::TileRec rec = { t->nodes.data(), t->x0, t->y0,
+                                        (int)F.maps.size(), 0 };
+                                F.tiles.push_back(rec);
+                                F.maps.push_back(map_desc(t));
+                                F.src.push_back(st->tile[c]);
+                                if (first == NULL) first = t;
+                                if ((t->nx != first->nx) || (t->ny != first->ny) ||
+                                    (t->dx != first->dx) || (t->dy != first->dy) ||
+                                    (t->z0 != first->z0) || (t->dz != first->dz) ||
+                                    (t->kind != first->kind))
+                                        S.uniform = 0;
+                        }
+                        if (first != NULL) {
+                                S.nx = first->nx;
+                                S.ny = first->ny;
+                                S.pitch = first->nx;
+                                S.kind = first->kind;
+                                S.dx = first->dx;
+                                S.dy = first->dy;
+                                S.z0 = first->z0;
+                                S.dz = first->dz;
+                                S.nx1 = (double)(first->nx - 1);
+                                S.ny1 = (double)(first->ny - 1);
+                        } else {
+                                S.uniform = 0;
                         }
                         if (st->tile.empty()) { /* empty stack: 1 cell, no tile */
                                 S.nlat = S.nlon = 1;
-                                F.tiles.push_back(-1);
+                                F.tiles.push_back(none);
                         }
+                        S.nlat_d = (double)S.nlat;
+                        S.nlon_d = (double)S.nlon;
                 }
         }
         G.geoid = -1;

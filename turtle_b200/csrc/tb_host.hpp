@@ -88,7 +88,7 @@ struct tb_flat_geometry {
         tb::Geometry G;
         std::vector<tb::MapDesc> maps;        /* nodes point to HOST memory */
         std::vector<struct turtle_map *> src; /* the map behind each descriptor */
-        std::vector<int> tiles;
+        std::vector<tb::TileRec> tiles;
 };
 
 /* ref: struct turtle_stepper, stepper.h:101-110 */

@@ -69,31 +69,37 @@ __device__ __forceinline__ bool finite3(const double v[3])
         return isfinite(v[0]) && isfinite(v[1]) && isfinite(v[2]);
 }
 
+/* Per-lane ray state of the trace kernel, kept in SHARED memory (structure of arrays,
+ * one column per thread: conflict free). Nothing of it is needed while a sample is
+ * being evaluated, so parking it here instead of in registers leaves the register
+ * file to the FP64 code of the sample: no spills at 6 CTAs per SM. */
+enum { F_POS = 0, F_DIR = 3, F_LAT = 6, F_LON, F_ALT, F_ELEV0, F_ELEV1, F_DS, F_DS0, F_DS1,
+       F_LEN, F_TOTAL = F_LEN + TURTLE_TRACE_MEDIA, F_LASTPOS, N_F = F_LASTPOS + 3 };
+enum { I_IDX0 = 0, I_IDX1, I_MEDIUM0, I_NSTEPS, I_NCHANGES, I_HASH, I_RAYLO, I_RAYHI, N_I };
+
+struct LaneStore {
+        double f[N_F][128];
+        int i[N_I][128];
+};
+
+__device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
+
 /* The persistent ray-tracing kernel. MINB = CTAs of 128 threads per SM the register
- * allocation is bounded for (occupancy vs spills is a measured trade). */
-template <bool LLA, int MINB>
+ * allocation is bounded for (occupancy vs registers is a measured trade). */
+template <bool LLA, bool PROJ, int MINB>
 __global__ void __launch_bounds__(128, MINB)
     trace_kernel(const __grid_constant__ tb::Geometry G, const TraceArgs A)
 {
-        const unsigned lane = threadIdx.x & 31u;
+        __shared__ LaneStore store;
+        const unsigned tid = threadIdx.x;
+        const unsigned lane = tid & 31u;
         const unsigned FULL = 0xffffffffu;
+#define SF(k) store.f[k][tid]
+#define SI(k) store.i[k][tid]
 
-        /* lane state: one ray */
-        double pos[3] = { 0., 0., 0. }, dir[3] = { 0., 0., 0. };
-        tb::Sample last;
-        last.lat = last.lon = last.alt = last.elev0 = last.elev1 = 0.;
-        last.idx0 = last.idx1 = -1;
-        double ds = 0., ds0 = 0., ds1 = 0.;
-        double len[TURTLE_TRACE_MEDIA] = { 0., 0., 0., 0. };
-        double total = 0.;
-        int medium0 = -1, mode = MODE_IDLE;
-        int n_steps = 0, n_changes = 0;
-        unsigned hash = 0u;
-        unsigned long long ray = 0ull;
-        double last_pos[3] = { DBL_MAX, DBL_MAX, DBL_MAX };
+        int mode = MODE_IDLE;
         tb::LlaState lla[LLA ? tb::MAX_TRANSFORMS : 1];
-
-        unsigned long long my_steps = 0ull, my_samples = 0ull;
+        unsigned my_steps = 0u, my_samples = 0u;
         bool exhausted = false;
 
         for (;;) {
@@ -110,19 +116,32 @@ __global__ void __launch_bounds__(128, MINB)
                                         const unsigned rank = __popc(idle & ((1u << lane) - 1u));
                                         const unsigned long long r = base + rank;
                                         if (r < A.n) {
-                                                ray = r;
                                                 const double * p = A.position + 3ull * r;
                                                 const double * d = A.direction + 3ull * r;
-                                                pos[0] = p[0]; pos[1] = p[1]; pos[2] = p[2];
-                                                dir[0] = d[0]; dir[1] = d[1]; dir[2] = d[2];
-                                                len[0] = len[1] = len[2] = len[3] = 0.;
-                                                total = 0.;
-                                                n_steps = n_changes = 0;
+                                                const double pos[3] = { p[0], p[1], p[2] };
+                                                const double dir[3] = { d[0], d[1], d[2] };
+                                                SF(F_POS) = pos[0];
+                                                SF(F_POS + 1) = pos[1];
+                                                SF(F_POS + 2) = pos[2];
+                                                SF(F_DIR) = dir[0];
+                                                SF(F_DIR + 1) = dir[1];
+                                                SF(F_DIR + 2) = dir[2];
+#pragma unroll
+                                                for (int m = 0; m < TURTLE_TRACE_MEDIA; m++)
+                                                        SF(F_LEN + m) = 0.;
+                                                SF(F_TOTAL) = 0.;
+                                                SI(I_NSTEPS) = 0;
+                                                SI(I_NCHANGES) = 0;
+                                                SI(I_RAYLO) = (int)(unsigned)(r & 0xffffffffull);
+                                                SI(I_RAYHI) = (int)(unsigned)(r >> 32);
                                                 mode = MODE_INIT;
                                                 /* every ray starts from a reset stepper
                                                  * (turtle_stepper_reset, stepper.c:647-651) */
-                                                last_pos[0] = last_pos[1] = last_pos[2] = DBL_MAX;
-                                                if (LLA) tb::lla_reset(lla, G.n_transforms);
+                                                if (LLA) {
+                                                        SF(F_LASTPOS) = SF(F_LASTPOS + 1) =
+                                                            SF(F_LASTPOS + 2) = DBL_MAX;
+                                                        tb::lla_reset(lla, G.n_transforms);
+                                                }
                                                 if (!finite3(pos) || !finite3(dir)) {
                                                         turtle_trace_result * R = A.results + r;
                                                         R->position[0] = pos[0];
@@ -151,73 +170,118 @@ __global__ void __launch_bounds__(128, MINB)
                 if (mode == MODE_IDLE) continue;
 
                 /* ---- exactly one geometry sample per lane and iteration ---- */
-                double p[3];
-                double ds2 = 0.;
-                if (mode == MODE_INIT) {
-                        p[0] = pos[0]; p[1] = pos[1]; p[2] = pos[2];
-                } else if (mode == MODE_TENT) { /* stepper.c:824 */
-                        p[0] = pos[0] + dir[0] * ds;
-                        p[1] = pos[1] + dir[1] * ds;
-                        p[2] = pos[2] + dir[2] * ds;
-                } else { /* stepper.c:840-844 */
-                        ds2 = 0.5 * (ds0 + ds1);
-                        p[0] = pos[0] + dir[0] * ds2;
-                        p[1] = pos[1] + dir[1] * ds2;
-                        p[2] = pos[2] + dir[2] * ds2;
-                }
                 tb::Sample S;
-                tb::sample_geometry<LLA>(G, lla, last_pos, mode != MODE_BISECT, p, S);
+                {
+                        double step = 0.; /* MODE_INIT: sample the start position */
+                        if (mode == MODE_TENT) /* stepper.c:824 */
+                                step = SF(F_DS);
+                        else if (mode == MODE_BISECT) /* stepper.c:840-844 */
+                                step = 0.5 * (SF(F_DS0) + SF(F_DS1));
+                        double p[3] = { SF(F_POS), SF(F_POS + 1), SF(F_POS + 2) };
+                        if (mode != MODE_INIT) {
+                                p[0] += SF(F_DIR) * step;
+                                p[1] += SF(F_DIR + 1) * step;
+                                p[2] += SF(F_DIR + 2) * step;
+                        }
+                        double last_pos[3] = { 0., 0., 0. };
+                        if (LLA) {
+                                last_pos[0] = SF(F_LASTPOS);
+                                last_pos[1] = SF(F_LASTPOS + 1);
+                                last_pos[2] = SF(F_LASTPOS + 2);
+                        }
+                        tb::sample_geometry<LLA, PROJ>(
+                            G, lla, last_pos, mode != MODE_BISECT, p, S);
+                        if (LLA && (mode != MODE_BISECT)) {
+                                SF(F_LASTPOS) = last_pos[0];
+                                SF(F_LASTPOS + 1) = last_pos[1];
+                                SF(F_LASTPOS + 2) = last_pos[2];
+                        }
+                }
+                compiler_fence(); /* keep the state loads below out of the sample code */
                 my_samples++;
 
                 /* ---- state update ------------------------------------------ */
                 bool settle = false;  /* a step (or the initial query) completed */
+                bool publish = false; /* S becomes stepper->last */
+                const int medium0 = SI(I_MEDIUM0);
+                double ds = SF(F_DS);
                 if (mode == MODE_INIT) {
-                        last = S;
-                        hash = (2166136261u ^ (unsigned)(S.idx0 + 1)) * 16777619u;
+                        publish = true;
+                        SI(I_HASH) = (int)((2166136261u ^ (unsigned)(S.idx0 + 1)) * 16777619u);
                         settle = true;
                 } else if (mode == MODE_TENT) {
-                        pos[0] = p[0]; pos[1] = p[1]; pos[2] = p[2];
-                        last = S;
+                        /* position += direction * ds, stepper.c:824 */
+                        SF(F_POS) += SF(F_DIR) * ds;
+                        SF(F_POS + 1) += SF(F_DIR + 1) * ds;
+                        SF(F_POS + 2) += SF(F_DIR + 2) * ds;
+                        publish = true;
                         if (S.idx0 != medium0) { /* stepper.c:832-838 */
-                                ds0 = -ds;
-                                ds1 = 0.;
+                                SF(F_DS0) = -ds;
+                                SF(F_DS1) = 0.;
                                 mode = MODE_BISECT;
-                                settle = !(ds1 - ds0 > 1E-08);
+                                settle = !(0. - (-ds) > 1E-08);
                         } else {
                                 settle = true;
                         }
                 } else {
+                        double ds0 = SF(F_DS0), ds1 = SF(F_DS1);
+                        const double ds2 = 0.5 * (ds0 + ds1);
                         if (S.idx0 == medium0) { /* stepper.c:848-859 */
                                 ds0 = ds2;
+                                SF(F_DS0) = ds0;
                         } else {
                                 ds1 = ds2;
-                                last = S;
-                                last_pos[0] = p[0]; last_pos[1] = p[1]; last_pos[2] = p[2];
+                                SF(F_DS1) = ds1;
+                                publish = true;
+                                if (LLA) { /* last.position = position2 */
+                                        SF(F_LASTPOS) = SF(F_POS) + SF(F_DIR) * ds2;
+                                        SF(F_LASTPOS + 1) = SF(F_POS + 1) + SF(F_DIR + 1) * ds2;
+                                        SF(F_LASTPOS + 2) = SF(F_POS + 2) + SF(F_DIR + 2) * ds2;
+                                }
                         }
                         if (!(ds1 - ds0 > 1E-08)) { /* stepper.c:861-863 */
                                 ds += ds1;
-                                pos[0] += dir[0] * ds1;
-                                pos[1] += dir[1] * ds1;
-                                pos[2] += dir[2] * ds1;
+                                SF(F_POS) += SF(F_DIR) * ds1;
+                                SF(F_POS + 1) += SF(F_DIR + 1) * ds1;
+                                SF(F_POS + 2) += SF(F_DIR + 2) * ds1;
                                 settle = true;
                         }
                 }
+                if (publish) {
+                        SF(F_LAT) = S.lat;
+                        SF(F_LON) = S.lon;
+                        SF(F_ALT) = S.alt;
+                        SF(F_ELEV0) = S.elev0;
+                        SF(F_ELEV1) = S.elev1;
+                        SI(I_IDX0) = S.idx0;
+                        SI(I_IDX1) = S.idx1;
+                }
                 if (!settle) continue;
 
+                tb::Sample last;
+                last.lat = SF(F_LAT);
+                last.lon = SF(F_LON);
+                last.alt = SF(F_ALT);
+                last.elev0 = SF(F_ELEV0);
+                last.elev1 = SF(F_ELEV1);
+                last.idx0 = SI(I_IDX0);
+                last.idx1 = SI(I_IDX1);
+                double total = SF(F_TOTAL);
+                int n_steps = SI(I_NSTEPS);
                 if (mode != MODE_INIT) {
                         /* example-stepper.c:136-139: length by STARTING medium */
                         const int m = (medium0 < TURTLE_TRACE_MEDIA - 1) ? medium0 :
                                                                            TURTLE_TRACE_MEDIA - 1;
-                        if (m == 0) len[0] += ds;
-                        else if (m == 1) len[1] += ds;
-                        else if (m == 2) len[2] += ds;
-                        else len[3] += ds;
+                        store.f[F_LEN + m][tid] += ds;
                         total += ds;
+                        SF(F_TOTAL) = total;
                         n_steps++;
+                        SI(I_NSTEPS) = n_steps;
                         my_steps++;
                         if (last.idx0 != medium0) {
-                                n_changes++;
-                                hash = (hash ^ (unsigned)(last.idx0 + 1)) * 16777619u;
+                                SI(I_NCHANGES) += 1;
+                                SI(I_HASH) = (int)(((unsigned)SI(I_HASH) ^
+                                                       (unsigned)(last.idx0 + 1)) * 16777619u);
                         }
                 }
 
@@ -232,38 +296,44 @@ __global__ void __launch_bounds__(128, MINB)
                         status = TURTLE_TRACE_STEPS;
 
                 if (status >= 0) {
+                        const unsigned long long ray =
+                            ((unsigned long long)(unsigned)SI(I_RAYHI) << 32) |
+                            (unsigned long long)(unsigned)SI(I_RAYLO);
                         turtle_trace_result * R = A.results + ray;
-                        R->position[0] = pos[0];
-                        R->position[1] = pos[1];
-                        R->position[2] = pos[2];
+                        R->position[0] = SF(F_POS);
+                        R->position[1] = SF(F_POS + 1);
+                        R->position[2] = SF(F_POS + 2);
                         R->altitude = last.alt;
-                        R->length[0] = len[0];
-                        R->length[1] = len[1];
-                        R->length[2] = len[2];
-                        R->length[3] = len[3];
+                        R->length[0] = SF(F_LEN);
+                        R->length[1] = SF(F_LEN + 1);
+                        R->length[2] = SF(F_LEN + 2);
+                        R->length[3] = SF(F_LEN + 3);
                         R->total = total;
                         R->n_steps = n_steps;
                         R->status = status;
                         R->index[0] = last.idx0;
                         R->index[1] = last.idx1;
-                        R->medium_hash = hash;
-                        R->n_changes = n_changes;
+                        R->medium_hash = (unsigned)SI(I_HASH);
+                        R->n_changes = SI(I_NCHANGES);
                         mode = MODE_IDLE;
                 } else {
-                        medium0 = last.idx0;
-                        ds = tb::step_length(G, last); /* stepper.c:798-813 */
+                        SI(I_MEDIUM0) = last.idx0;
+                        SF(F_DS) = tb::step_length(G, last); /* stepper.c:798-813 */
                         mode = MODE_TENT;
                 }
         }
+#undef SF
+#undef SI
 
         /* per-warp counters */
+        unsigned long long steps64 = my_steps, samples64 = my_samples;
         for (int o = 16; o > 0; o >>= 1) {
-                my_steps += __shfl_down_sync(FULL, my_steps, o);
-                my_samples += __shfl_down_sync(FULL, my_samples, o);
+                steps64 += __shfl_down_sync(FULL, steps64, o);
+                samples64 += __shfl_down_sync(FULL, samples64, o);
         }
         if (lane == 0u) {
-                atomicAdd(A.cursor + 1, my_steps);
-                atomicAdd(A.cursor + 2, my_samples);
+                atomicAdd(A.cursor + 1, steps64);
+                atomicAdd(A.cursor + 2, samples64);
         }
 }
 
@@ -515,7 +585,7 @@ struct turtle_plan {
         tb::Geometry G; /* device pointers */
         void * pool;    /* every tile of the plan, one allocation */
         tb::MapDesc * d_maps;
-        int * d_tiles;
+        tb::TileRec * d_tiles;
         size_t bytes;
         std::vector<struct turtle_stack *> pinned;
         unsigned long long * d_counters; /* N_SLOTS + 1 triplets */
@@ -644,14 +714,18 @@ extern "C" enum turtle_return turtle_stepper_freeze(
                 if (first[F.src[i]] == i) err = upload_nodes(dst, pitch[i], F.src[i]);
         }
         const size_t maps_bytes = std::max<size_t>(n_maps, 1) * sizeof(tb::MapDesc);
-        const size_t tiles_bytes = std::max<size_t>(F.tiles.size(), 1) * sizeof(int);
+        const size_t tiles_bytes = std::max<size_t>(F.tiles.size(), 1) * sizeof(tb::TileRec);
+        /* device copies of the tile records: device node pointers and padded pitch */
+        std::vector<tb::TileRec> tiles = F.tiles;
+        for (size_t i = 0; i < tiles.size(); i++)
+                if (tiles[i].map >= 0) tiles[i].nodes = maps[tiles[i].map].nodes;
         if (err == cudaSuccess) err = cudaMalloc((void **)&plan->d_maps, maps_bytes);
         if ((err == cudaSuccess) && n_maps)
                 err = cudaMemcpy(plan->d_maps, maps.data(), n_maps * sizeof(tb::MapDesc),
                     cudaMemcpyHostToDevice);
         if (err == cudaSuccess) err = cudaMalloc((void **)&plan->d_tiles, tiles_bytes);
-        if ((err == cudaSuccess) && !F.tiles.empty())
-                err = cudaMemcpy(plan->d_tiles, F.tiles.data(), F.tiles.size() * sizeof(int),
+        if ((err == cudaSuccess) && !tiles.empty())
+                err = cudaMemcpy(plan->d_tiles, tiles.data(), tiles.size() * sizeof(tb::TileRec),
                     cudaMemcpyHostToDevice);
         if (err == cudaSuccess)
                 err = cudaMalloc((void **)&plan->d_counters,
@@ -665,6 +739,16 @@ extern "C" enum turtle_return turtle_stepper_freeze(
         plan->G = F.G;
         plan->G.maps = plan->d_maps;
         plan->G.tiles = plan->d_tiles;
+        for (int k = 0; k < plan->G.n_stacks; k++) { /* the device pitch is padded */
+                tb::StackDesc & S = plan->G.stacks[k];
+                for (int c = 0; c < S.nlat * S.nlon; c++) {
+                        const int id = tiles[S.tile0 + c].map;
+                        if (id >= 0) {
+                                S.pitch = maps[id].pitch;
+                                break;
+                        }
+                }
+        }
         plan->bytes = pool_bytes + maps_bytes + tiles_bytes;
         *plan_ = plan;
         return TURTLE_RETURN_SUCCESS;
@@ -713,7 +797,7 @@ static int trace_grid(const struct turtle_plan * plan, size_t n, int * blocks, i
 {
         *threads = (plan->threads > 0) ? round_up(plan->threads, 32) : 128;
         if (*threads > 128) *threads = 128; /* __launch_bounds__(128, .) */
-        const int per_sm = (plan->ctas_per_sm > 0) ? plan->ctas_per_sm : 4;
+        const int per_sm = (plan->ctas_per_sm > 0) ? plan->ctas_per_sm : 6;
         long long want = (long long)plan->sm_count * per_sm;
         const long long need = (long long)((n + *threads - 1) / *threads);
         if (need < want) want = (need > 0) ? need : 1;
@@ -750,18 +834,23 @@ static cudaError_t launch_trace(struct turtle_plan * plan, size_t n, const doubl
         int blocks, threads;
         const int per_sm = trace_grid(plan, n, &blocks, &threads);
         const bool lla = plan->G.range > 0.;
+        bool proj = false; /* any projected map? else the projection code is compiled out */
+        for (int t = 0; t < plan->G.n_transforms; t++)
+                if (plan->G.transforms[t].type != tb::PROJ_GEODETIC) proj = true;
 #define TRACE_LAUNCH(MINB)                                                             \
         do {                                                                           \
-                if (lla)                                                               \
-                        trace_kernel<true, MINB><<<blocks, threads, 0, stream>>>(plan->G, A);  \
+                if (lla && proj)                                                       \
+                        trace_kernel<true, true, MINB><<<blocks, threads, 0, stream>>>(plan->G, A);   \
+                else if (lla)                                                          \
+                        trace_kernel<true, false, MINB><<<blocks, threads, 0, stream>>>(plan->G, A);  \
+                else if (proj)                                                         \
+                        trace_kernel<false, true, MINB><<<blocks, threads, 0, stream>>>(plan->G, A);  \
                 else                                                                   \
-                        trace_kernel<false, MINB><<<blocks, threads, 0, stream>>>(plan->G, A); \
+                        trace_kernel<false, false, MINB><<<blocks, threads, 0, stream>>>(plan->G, A); \
         } while (0)
         /* the register budget follows the requested residency (in units of 128 threads) */
         const int minb = per_sm * threads / 128;
-        if (minb <= 3)
-                TRACE_LAUNCH(3);
-        else if (minb == 4)
+        if (minb <= 4)
                 TRACE_LAUNCH(4);
         else if (minb == 5)
                 TRACE_LAUNCH(5);
@@ -1247,6 +1336,8 @@ static enum turtle_return map_mirror(turtle_function_t * fn, struct turtle_map *
         desc->dy = map->dy;
         desc->z0 = map->z0;
         desc->dz = map->dz;
+        desc->nx1 = (double)(map->nx - 1);
+        desc->ny1 = (double)(map->ny - 1);
         return TURTLE_RETURN_SUCCESS;
 }
 
