@@ -195,6 +195,9 @@ TURTLE_API enum turtle_return turtle_map_elevation_ecef_batch_device(
  * Stops at the first node that turtle_map_fill rejects and returns its code. */
 TURTLE_API enum turtle_return turtle_map_fill_batch(
     struct turtle_map * map, const double * elevation);
+/* Same for rows [iy0, iy0 + n_rows): elevation[(iy - iy0) * nx + ix]. */
+TURTLE_API enum turtle_return turtle_map_fill_rows(
+    struct turtle_map * map, int iy0, int n_rows, const double * elevation);
 
 /* ---- device utilities -------------------------------------------------------*/
 /* Number of CUDA devices visible (0 when there is no driver / GPU). */
@@ -203,6 +206,10 @@ TURTLE_API int turtle_b200_device_count(void);
  * dependent-chain DFMA micro-benchmark kernel; used as the compute roofline. */
 TURTLE_API double turtle_b200_dfma_peak(int repeats);
 TURTLE_API const char * turtle_b200_version(void);
+/* Device self test of the shared-reciprocal division used by the kernels against the
+ * compiler's IEEE division on 2 * n random operand pairs: number of results that
+ * differ in any bit (0 expected), -1 without a device. */
+TURTLE_API long long turtle_b200_selftest_division(size_t n, uint64_t seed);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,324 @@
+"""Measure the other BASELINE.json configurations (bench.py covers configs[1] = C2):
+
+  c1  1 Mi straight rays from one station through a 2001 x 2001 UTM map + flat bottom
+  c3  random rays through a layered stepper: Lambert map over a 3x3 tile stack over a
+      flat geoid, local approximation on (range 10 m)
+  c4  particles x 100 random-walk steps (turtle_stepper_step_batch with device states)
+  c5  batched turtle_ecef_to_geodetic + turtle_map_elevation on a 20k x 20k map
+
+    python tools/bench_configs.py --config c1 [--rays N] [--steps K]
+
+Each run prints ONE JSON line: throughput on the GPU (CUDA events on the launching
+stream, inputs resident in HBM), the reference's CPU path on all host cores over a
+strided sample of the same inputs, and the parity of that sample. SURVEY.md section 8d
+defines the workloads. Development / evidence tool: results are kept under profiles/.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import bench as B  # noqa: E402
+import turtle_b200 as tb  # noqa: E402
+from oracle import harness as H  # noqa: E402
+from tests.common import Scene, compare_traces  # noqa: E402
+from turtle_b200 import synth  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def timed(fn, steps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def trace_config(name, scene, pos, dirs, rule_o, rule_g, args, ops_per_sample, note):
+    stepper, maps, stacks = scene.product()
+    plan = stepper.freeze(0)
+    n = len(pos)
+    d_pos, d_dir = torch.from_numpy(pos).to(DEV), torch.from_numpy(dirs).to(DEV)
+    d_res = torch.empty((n, 96), dtype=torch.uint8, device=DEV)
+    ms = timed(lambda: plan.trace_device(n, d_pos, d_dir, rule_g, d_res), args.steps)
+    c = plan.counters(sync=True)
+    got = d_res.cpu().numpy().view(tb.TRACE_RESULT).reshape(n)
+    # reference on all cores, strided sample
+    stride = max(1, n // args.cpu_rays)
+    ora = scene.oracle(locked=True)
+    want, steps, seconds = ora.trace(pos[::stride], dirs[::stride], rule_o,
+                                     threads=os.cpu_count())
+    rep = compare_traces(want, got[::stride])
+    dfma = tb.dfma_peak(3)
+    achieved = ops_per_sample * c["samples"] / (ms * 1e-3) / 1e12
+    line = {
+        "config": name, "workload": note, "rays": n, "ms_per_step": ms,
+        "Mrays_per_s": n / ms / 1e3, "ns_per_step": ms * 1e6 / max(c["steps"], 1),
+        "steps_per_ray": c["steps"] / n, "samples_per_step": c["samples"] / max(c["steps"], 1),
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": dfma / 1e3,
+                     "unit": "Tinst/s (FP64 pipe; FMA = 1)", "frac": achieved / (dfma / 1e3),
+                     "ops_per_sample": ops_per_sample},
+        "cpu_baseline": {"Mrays_per_s": len(want) / seconds / 1e6, "cores": os.cpu_count(),
+                         "ns_per_step": 1e9 * seconds / max(steps, 1), "kind": "reference"
+                         if H.best_oracle() == H.REF else "port",
+                         "sample": "every %d-th ray (%d rays)" % (stride, len(want))},
+        "parity": rep, "status_counts": np.bincount(got["status"], minlength=5).tolist(),
+        "plan_bytes": plan.bytes,
+    }
+    line["speedup_vs_cpu"] = line["Mrays_per_s"] / line["cpu_baseline"]["Mrays_per_s"]
+    print(json.dumps(line), flush=True)
+
+
+def c1(args):
+    n_map = 2001
+    x = (486000., 506000.)
+    y = (5057000., 5077000.)
+    vals = synth.fbm_grid(np.arange(n_map) / 3., np.arange(n_map) / 3.) * 3000.
+    mp = dict(nx=n_map, ny=n_map, x=x, y=y, z=(0., 3000.), projection="UTM 31N", values=vals)
+    scene = Scene(maps=[mp], ops=[(H.ADD_FLAT, 0, -100.), (H.ADD_LAYER, 0, 0.),
+                                  (H.ADD_MAP, 0, 0.)], range=args.range)
+    ora = scene.oracle()
+    lat, lon = ora.project("UTM 31N", [0.5 * (x[0] + x[1])], [0.5 * (y[0] + y[1])], inverse=True)
+    origin, idx = ora.position(lat, lon, [1.0], 1)
+    n = args.rays or (1 << 20)
+    az, el = synth.golden_fan(n)
+    dirs = synth.np_from_horizontal(np.full(n, lat[0]), np.full(n, lon[0]), az, el)
+    pos = np.repeat(origin, n, 0)
+    # UTM map sample = geodetic transform (~340) + UTM projection (~810) + bilinear
+    trace_config("c1", scene, pos, dirs, H.rule(3100.), tb.trace_rule(3100.), args, 1190.,
+                 "1 Mi-ray fan from the centre of a 2001x2001 UTM 31N map (10 m pitch) over a "
+                 "flat bottom at -100 m, range %g, stop alt > 3100 m | 1e5 steps" % args.range)
+
+
+def layered_scene(rg):
+    B.make_stack()
+    d0 = H.Driver(H.best_oracle())
+    n_map = 2001
+    cx, cy = d0.project("Lambert 93", [46.5], [3.5])
+    half = 5. * (n_map - 1) / 2
+    x = (cx[0] - half, cx[0] + half)
+    y = (cy[0] - half, cy[0] + half)
+    X, Y = np.meshgrid(np.linspace(x[0], x[1], n_map), np.linspace(y[0], y[1], n_map))
+    la, lo = d0.project("Lambert 93", X.ravel(), Y.ravel(), inverse=True)
+    vals = np.rint(synth.fbm_points((lo - B.STACK_LON0) * 3600., (la - B.STACK_LAT0) * 3600.)
+                   * 3000.) + 0.
+    mp = dict(nx=n_map, ny=n_map, x=x, y=y, z=(0., 6553.5), projection="Lambert 93", values=vals)
+    return Scene(maps=[mp], stacks=[B.stack_dir()],
+                 ops=[(H.ADD_FLAT, 0, 0.), (H.ADD_STACK, 0, 0.), (H.ADD_MAP, 0, 0.)], range=rg)
+
+
+def c3(args):
+    scene = layered_scene(10. if args.range is None else args.range)
+    n = args.rays or (1 << 24)
+    lat = B.STACK_LAT0 - 0.1 + (B.STACK_N + 0.2) * synth.random_uniform(n, 0xC3, 0)
+    lon = B.STACK_LON0 - 0.1 + (B.STACK_N + 0.2) * synth.random_uniform(n, 0xC3, 1)
+    alt = -500. + 5500. * synth.random_uniform(n, 0xC3, 2)
+    pos = synth.np_ecef_from_geodetic(lat, lon, alt)
+    dirs = synth.random_unit(n, 0xC3)
+    # per sample: geodetic transform + stack lookup; the Lambert map is only evaluated
+    # inside its 10 km footprint -> ~385 FP64 instructions on average
+    trace_config("c3", scene, pos, dirs, H.rule(9000., length_max=1e5),
+                 tb.trace_rule(9000., length_max=1e5), args, 385.,
+                 "random rays (origins in the stack bbox + 0.1 deg, alt -500..5000 m, isotropic) "
+                 "through flat(0) / 3x3 SRTMGL1 stack / 2001x2001 Lambert-93 map (5 m), range "
+                 "%g, stop leaves data | alt > 9000 m | path > 100 km | 1e5 steps" % scene.range)
+
+
+def c4(args):
+    scene = layered_scene(1. if args.range is None else args.range)
+    stepper, maps, stacks = scene.product()
+    plan = stepper.freeze(0)
+    n = args.rays or (1 << 23)
+    k = args.walk
+    lat = 45.5 + 2. * synth.random_uniform(n, 0xC4, 0)
+    lon = 2.5 + 2. * synth.random_uniform(n, 0xC4, 1)
+    h = -50. + 100. * synth.random_uniform(n, 0xC4, 2)
+    origin, idx = plan.position(lat, lon, h, 0)
+    assert (idx >= 0).all()
+    d_pos0 = torch.from_numpy(origin).to(DEV)
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(0xC4)
+
+    def directions():
+        u = torch.rand((n, 2), generator=gen, device=DEV, dtype=torch.float64)
+        cz = 2 * u[:, 0] - 1
+        sz = torch.sqrt(torch.clamp(1 - cz * cz, min=0))
+        ph = 2 * np.pi * u[:, 1]
+        return torch.stack([sz * torch.cos(ph), sz * torch.sin(ph), cz], 1).contiguous()
+
+    stride = max(1, n // args.cpu_rays)
+    states = plan.states(n)
+    d_step = torch.empty(n, dtype=torch.float64, device=DEV)
+    d_alt = torch.empty(n, dtype=torch.float64, device=DEV)
+    d_idx = torch.empty((n, 2), dtype=torch.int32, device=DEV)
+    total_ms, sample_dirs, got_step, got_alt, got_idx = 0., [], [], [], []
+    for rep in range(2):  # pass 0 = warm-up, pass 1 = timed
+        states.reset()
+        d_pos = d_pos0.clone()
+        gen.manual_seed(0xC4)
+        total_ms = 0.
+        sample_dirs, got_step, got_alt, got_idx = [], [], [], []
+        for j in range(k):
+            d_dir = directions()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            plan.step_device(n, d_pos, d_dir, states=states, altitude=d_alt, step=d_step, index=d_idx)
+            e1.record()
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+            if rep == 1:
+                sample_dirs.append(d_dir[::stride].cpu().numpy())
+                got_step.append(d_step[::stride].cpu().numpy())
+                got_alt.append(d_alt[::stride].cpu().numpy())
+                got_idx.append(d_idx[::stride].cpu().numpy())
+    ora = scene.oracle(locked=True)
+    want = ora.walk(origin[::stride], np.stack(sample_dirs), threads=os.cpu_count())
+    gs, ga, gi = np.stack(got_step), np.stack(got_alt), np.stack(got_idx)
+    same_idx = (gi == want["index"]).all(2)
+    ok = np.logical_and.accumulate(same_idx, 0)  # particle still on the oracle's track
+    m = origin[::stride].shape[0]
+    line = {
+        "config": "c4", "workload": "%d particles x %d turtle_stepper_step, fresh isotropic "
+        "direction each step, start within +-50 m of the ground; geometry of c3, range %g, "
+        "per-particle stepper state on the device" % (n, k, scene.range),
+        "particles": n, "walk_steps": k, "ms_total": total_ms,
+        "Msteps_per_s": n * k / total_ms / 1e3, "ns_per_step": total_ms * 1e6 / (n * k),
+        "state_bytes_per_particle": 976,
+        "cpu_baseline": {"Msteps_per_s": m * k / want["seconds"] / 1e6, "cores": os.cpu_count(),
+                         "ns_per_step": 1e9 * want["seconds"] / (m * k),
+                         "sample": "every %d-th particle (%d particles)" % (stride, m)},
+        "parity": {"particles": int(m), "off_track_particles": int((~ok[-1]).sum()),
+                   "max_step_abs_diff_m": float(np.abs(gs - want["step"])[ok].max()),
+                   "max_altitude_abs_diff_m": float(np.abs(ga - want["altitude"])[ok].max()),
+                   "bit_identical_steps_frac": float((gs == want["step"])[ok].mean())},
+    }
+    line["speedup_vs_cpu"] = line["Msteps_per_s"] / line["cpu_baseline"]["Msteps_per_s"]
+    print(json.dumps(line), flush=True)
+
+
+def c5(args):
+    n_map = args.map_nodes
+    box = 5.5
+    lat0, lon0 = 44., 1.
+    # 20k x 20k nodes: a cheap separable synthetic terrain keeps the host fill tractable
+    gx = np.arange(n_map, dtype=np.float64)
+    row = 2500. + 1000. * np.sin(gx * 0.013) + 300. * np.sin(gx * 0.171)
+    col = 400. * np.cos(gx * 0.007) + 100. * np.sin(gx * 0.31)
+    t0 = time.time()
+    mp = tb.Map(n_map, n_map, (lon0, lon0 + box), (lat0, lat0 + box), (0., 65535.), None)
+    chunk = 1000
+    import ctypes as C
+    from turtle_b200._lib import lib
+    for j0 in range(0, n_map, chunk):
+        j1 = min(n_map, j0 + chunk)
+        block = np.ascontiguousarray(np.rint(row[None, :] + col[j0:j1, None]))
+        tb.api._check(lib.turtle_map_fill_rows(mp.handle, j0, j1 - j0,
+                                               block.ctypes.data_as(C.c_void_p)))
+    fill_s = time.time() - t0
+    n = args.rays or (1 << 30)
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(0xC5)
+    d_ecef = torch.empty((n, 3), dtype=torch.float64, device=DEV)
+    piece = 1 << 26
+    for i0 in range(0, n, piece):
+        m = min(piece, n - i0)
+        u = torch.rand((3, m), generator=gen, device=DEV, dtype=torch.float64)
+        la = (lat0 - 0.05 + (box + 0.1) * u[0]).contiguous()
+        lo = (lon0 - 0.05 + (box + 0.1) * u[1]).contiguous()
+        al = (5000. * u[2]).contiguous()
+        tb.api._check(lib.turtle_ecef_from_geodetic_batch_device(
+            m, la.data_ptr(), lo.data_ptr(), al.data_ptr(), d_ecef[i0:].data_ptr(), None))
+        torch.cuda.synchronize()
+    d_lat = torch.empty(n, dtype=torch.float64, device=DEV)
+    d_lon = torch.empty(n, dtype=torch.float64, device=DEV)
+    d_alt = torch.empty(n, dtype=torch.float64, device=DEV)
+    d_z = torch.zeros(n, dtype=torch.float64, device=DEV)
+    d_in = torch.zeros(n, dtype=torch.int32, device=DEV)
+    P = lambda t: t.data_ptr()  # noqa: E731
+    ms_geo = timed(lambda: tb.api._check(lib.turtle_ecef_to_geodetic_batch_device(
+        n, P(d_ecef), P(d_lat), P(d_lon), P(d_alt), None)), args.steps)
+    ms_map = timed(lambda: tb.api._check(lib.turtle_map_elevation_batch_device(
+        mp.handle, n, P(d_lon), P(d_lat), P(d_z), P(d_in), None)), args.steps)
+    z_two = d_z[::4096].cpu().numpy().copy()
+    ms_fused = timed(lambda: tb.api._check(lib.turtle_map_elevation_ecef_batch_device(
+        mp.handle, n, P(d_ecef), P(d_lat), P(d_lon), P(d_alt), P(d_z), P(d_in), None)), args.steps)
+    # oracle on a strided sample
+    stride = max(1, n // args.cpu_rays)
+    ecef_s = d_ecef[::stride].cpu().numpy()
+    ora = H.Driver(H.best_oracle())
+    t0 = time.time()
+    wla, wlo, wal = ora.ecef_to_geodetic(ecef_s)
+    t_geo = time.time() - t0
+    gla, glo, gal = d_lat[::stride].cpu().numpy(), d_lon[::stride].cpu().numpy(), \
+        d_alt[::stride].cpu().numpy()
+    gz, gin = d_z[::stride].cpu().numpy(), d_in[::stride].cpu().numpy()
+    # elevation of the oracle's own lat / lon through the product's scalar host call
+    # (bit-identical to the reference on maps, tests/test_oracle.py)
+    hz = np.zeros(len(wla))
+    hin = np.zeros(len(wla), dtype=np.int32)
+    zz, ii = C.c_double(), C.c_int()
+    for i in range(min(len(wla), 200000)):
+        lib.turtle_map_elevation(mp.handle, wlo[i], wla[i], C.byref(zz), C.byref(ii))
+        hz[i], hin[i] = zz.value, ii.value
+    m = min(len(wla), 200000)
+    both = (hin[:m] == 1) & (gin[:m] == 1)
+    hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) \
+        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.
+    dfma = tb.dfma_peak(3)
+
+    def roof(ms, nbytes, ops):
+        return {"GB_per_s": n * nbytes / ms / 1e6, "hbm_frac": n * nbytes / ms / 1e6 / hbm,
+                "fp64_Tinst_per_s": n * ops / ms / 1e9, "fp64_frac": n * ops / ms / 1e9 / (dfma / 1e3)}
+    line = {
+        "config": "c5", "workload": "%d ECEF points (uniform over the map box + 0.05 deg, alt "
+        "0-5000 m) -> turtle_ecef_to_geodetic_batch, turtle_map_elevation_batch and the fused "
+        "kernel on a %dx%d uint16 geodetic map (%.0f MB)" % (n, n_map, n_map, n_map * n_map * 2 / 1e6),
+        "points": n, "map_fill_seconds": fill_s,
+        "to_geodetic": dict(ms=ms_geo, Gpoints_per_s=n / ms_geo / 1e6, **roof(ms_geo, 48, 340)),
+        "map_elevation": dict(ms=ms_map, Gpoints_per_s=n / ms_map / 1e6, **roof(ms_map, 36, 70)),
+        "fused": dict(ms=ms_fused, Gpoints_per_s=n / ms_fused / 1e6, **roof(ms_fused, 68, 410)),
+        "peaks": {"hbm_GB_per_s": hbm, "fp64_Tinst_per_s": dfma / 1e3},
+        "cpu_baseline": {"to_geodetic_Mpoints_per_s_1core": len(wla) / t_geo / 1e6,
+                         "sample": "every %d-th point (%d points), 1 thread" % (stride, len(wla))},
+        "parity": {"points": int(len(wla)), "altitude_bit_exact": bool(np.array_equal(wal, gal)),
+                   "lat_max_ulp": int(np.abs(wla.view(np.int64) - gla.view(np.int64)).max()),
+                   "lon_max_ulp": int(np.abs(wlo.view(np.int64) - glo.view(np.int64)).max()),
+                   "inside_flips": int((hin[:m] != gin[:m]).sum()),
+                   "elevation_max_abs_diff_m": float(np.abs(hz[:m] - gz[:m])[both].max()),
+                   "fused_equals_two_pass": bool(np.array_equal(z_two, d_z[::4096].cpu().numpy()))},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", required=True, choices=["c1", "c3", "c4", "c5"])
+    ap.add_argument("--rays", type=int, default=0)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--range", type=float, default=None)
+    ap.add_argument("--walk", type=int, default=100)
+    ap.add_argument("--cpu-rays", type=int, default=1 << 18)
+    ap.add_argument("--map-nodes", type=int, default=20000)
+    args = ap.parse_args()
+    if args.config == "c1" and args.range is None:
+        args.range = 0.
+    {"c1": c1, "c3": c3, "c4": c4, "c5": c5}[args.config](args)
+
+
+if __name__ == "__main__":
+    main()

@@ -130,10 +130,12 @@ SIGNATURES = {
     "turtle_map_elevation_ecef_batch": (_I, [_P, _N, _P, _P, _P, _P, _P, _P]),
     "turtle_map_elevation_ecef_batch_device": (_I, [_P, _N, _P, _P, _P, _P, _P, _P, _P]),
     "turtle_map_fill_batch": (_I, [_P, _P]),
+    "turtle_map_fill_rows": (_I, [_P, _I, _I, _P]),
     # utilities
     "turtle_b200_device_count": (_I, []),
     "turtle_b200_dfma_peak": (_D, [_I]),
     "turtle_b200_version": (C.c_char_p, []),
+    "turtle_b200_selftest_division": (C.c_longlong, [_N, C.c_uint64]),
 }
 
 

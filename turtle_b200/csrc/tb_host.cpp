@@ -555,18 +555,25 @@ extern "C" enum turtle_return turtle_map_fill(
         return TURTLE_RETURN_SUCCESS;
 }
 
-/* Bulk variant of turtle_map_fill (turtle_b200.h). */
+/* Bulk variants of turtle_map_fill (turtle_b200.h). */
+extern "C" enum turtle_return turtle_map_fill_rows(
+    struct turtle_map * map, int iy0, int n_rows, const double * elevation)
+{
+        if (map == NULL) return turtle_map_fill(map, 0, 0, 0.);
+        for (int iy = iy0; iy < iy0 + n_rows; iy++)
+                for (int ix = 0; ix < map->nx; ix++) {
+                        enum turtle_return rc = turtle_map_fill(
+                            map, ix, iy, elevation[(size_t)(iy - iy0) * map->nx + ix]);
+                        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+                }
+        return TURTLE_RETURN_SUCCESS;
+}
+
 extern "C" enum turtle_return turtle_map_fill_batch(
     struct turtle_map * map, const double * elevation)
 {
         if (map == NULL) return turtle_map_fill(map, 0, 0, 0.);
-        for (int iy = 0; iy < map->ny; iy++)
-                for (int ix = 0; ix < map->nx; ix++) {
-                        enum turtle_return rc = turtle_map_fill(
-                            map, ix, iy, elevation[(size_t)iy * map->nx + ix]);
-                        if (rc != TURTLE_RETURN_SUCCESS) return rc;
-                }
-        return TURTLE_RETURN_SUCCESS;
+        return turtle_map_fill_rows(map, 0, map->ny, elevation);
 }
 
 extern "C" enum turtle_return turtle_map_node(const struct turtle_map * map, int ix,

@@ -552,6 +552,49 @@ __global__ void __launch_bounds__(256) map_elevation_ecef_kernel(const tb::MapDe
         }
 }
 
+/* ---- self test of tb::divide against the compiler's IEEE division ---------------- */
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x)
+{
+        x += 0x9E3779B97F4A7C15ull;
+        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+        x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+        return x ^ (x >> 31);
+}
+
+/* Random operands: full 52-bit significands, binary exponents in [lo, hi]. */
+__device__ __forceinline__ double random_double(unsigned long long k, int lo, int hi)
+{
+        const unsigned long long r = mix64(k);
+        const int e = lo + (int)((r >> 52) % (unsigned)(hi - lo + 1));
+        const unsigned long long bits = ((unsigned long long)(1023 + e) << 52) |
+            (r & 0xFFFFFFFFFFFFFull) | ((mix64(k ^ 0x5bd1e995ull) & 1ull) << 63);
+        return __longlong_as_double((long long)bits);
+}
+
+__global__ void divide_selftest_kernel(unsigned long long n, unsigned long long seed,
+    unsigned long long * mismatches)
+{
+        const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+        unsigned long long bad = 0ull;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+             i < n; i += stride) {
+                const double a = random_double(seed + 2ull * i, -60, 60);
+                const double b = fabs(random_double(seed + 2ull * i + 1ull, -60, 60));
+                const tb::Divisor d = tb::make_divisor(b);
+                const double q1 = tb::divide(a, d);
+                const double q2 = a / b;
+                if (__double_as_longlong(q1) != __double_as_longlong(q2)) bad++;
+                /* a second numerator against the same divisor, and exact cases */
+                const double a2 = a * 0.75 + 1.0;
+                if (__double_as_longlong(tb::divide(a2, d)) != __double_as_longlong(a2 / b)) bad++;
+                if (tb::divide(0., d) != 0. || tb::divide(b, d) != 1.) bad++;
+                const int k = (int)(mix64(i) & 0xffff) - 32768;
+                if (tb::int_to_double(k) != (double)k) bad++;
+        }
+        if (bad) atomicAdd(mismatches, bad);
+}
+
 /* ---- FP64 FMA peak (roofline denominator of the stepper) --------------------- */
 
 __global__ void __launch_bounds__(256) dfma_kernel(double * out, int iterations)
@@ -633,6 +676,22 @@ extern "C" int turtle_b200_device_count(void)
 }
 
 extern "C" const char * turtle_b200_version(void) { return "turtle-b200 0.1 (sm_100a)"; }
+
+/* Device self test: tb::divide (shared reciprocal, tb_core.cuh) against `a / b` on
+ * 2 * n random operand pairs; returns the number of results that differ in any bit
+ * (must be 0), or -1 without a device. */
+extern "C" long long turtle_b200_selftest_division(size_t n, uint64_t seed)
+{
+        if (turtle_b200_device_count() == 0) return -1;
+        unsigned long long * d_bad = NULL;
+        unsigned long long bad = 0ull;
+        if (cudaMalloc((void **)&d_bad, sizeof(bad)) != cudaSuccess) return -1;
+        cudaMemset(d_bad, 0x0, sizeof(bad));
+        divide_selftest_kernel<<<148 * 8, 256>>>(n, seed, d_bad);
+        cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
+        cudaFree(d_bad);
+        return (cudaGetLastError() == cudaSuccess) ? (long long)bad : -1;
+}
 
 /* Copy a host grid into the device pool with a padded pitch. */
 static cudaError_t upload_nodes(uint16_t * dst, int pitch, const struct turtle_map * map)
