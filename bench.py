@@ -10,8 +10,9 @@ leaves the stack (index[0] < 0), rises above 9000 m or after 1e5 steps.
 
 One "step" of this bench = one pass of the hot path over the whole batch of rays of
 every rank. Scaling is weak: each rank (one per GPU, DEM replicated) traces its own
-16 Mi-ray fan (rank r looks from a detector shifted by r * 0.01 degrees); rank 0 then
-gathers the 96-byte result records of all ranks over NCCL, inside the timed region.
+16 Mi rays -- with N ranks the fan has N x 4096 azimuths and rank r takes azimuths
+r, r + N, ... --; rank 0 then gathers the 96-byte result records of all ranks over
+NCCL, inside the timed region.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--rays R] [--impl reference]
 
@@ -60,20 +61,20 @@ def make_stack():
     return synth.write_hgt_stack(stack_dir(), STACK_LAT0, STACK_LON0, STACK_N, STACK_N, n=3601)
 
 
-def fan(rank, first, count, n_az=N_AZ, n_el=N_EL):
-    """Directions of rays [first, first + count) of the fan of `rank`."""
+def fan(rank, world, first, count, n_az=N_AZ, n_el=N_EL):
+    """Directions of rays [first, first + count) of the part of the fan traced by `rank`:
+    the azimuths of the `world` ranks interleave into one fan of world * n_az azimuths."""
     from turtle_b200 import synth
-    lat, lon = DET_LAT + 0.01 * rank, DET_LON + 0.01 * rank
-    return lat, lon, synth.fan_directions(lat, lon, n_az, n_el, first=first, count=count)
+    return DET_LAT, DET_LON, synth.fan_directions(
+        DET_LAT, DET_LON, n_az, n_el, first=first, count=count, part=rank, parts=world)
 
 
-def fan_subsample(rank, stride, n_total):
-    """Every `stride`-th ray of the fan (ray index order preserved)."""
+def fan_subsample(rank, world, stride, n_total):
+    """Every `stride`-th ray of the rank's part of the fan (ray index order preserved)."""
     from turtle_b200 import synth
-    lat, lon = DET_LAT + 0.01 * rank, DET_LON + 0.01 * rank
     r = np.arange(0, n_total, stride, dtype=np.int64)
-    az, el = synth.fan_angles(r, N_AZ, N_EL)
-    return synth.np_from_horizontal(np.full(len(r), lat), np.full(len(r), lon), az, el)
+    az, el = synth.fan_angles(r, N_AZ, N_EL, part=rank, parts=world)
+    return synth.np_from_horizontal(np.full(len(r), DET_LAT), np.full(len(r), DET_LON), az, el)
 
 
 class ClockSampler:
@@ -129,10 +130,9 @@ def reference_driver():
     return d, H, kind
 
 
-def cpu_trace(d, H, rank, stride, n_total, cores):
-    lat, lon = DET_LAT + 0.01 * rank, DET_LON + 0.01 * rank
-    pos, _ = d.position([lat], [lon], [DET_HEIGHT], 0)
-    dirs = fan_subsample(rank, stride, n_total)
+def cpu_trace(d, H, rank, world, stride, n_total, cores):
+    pos, _ = d.position([DET_LAT], [DET_LON], [DET_HEIGHT], 0)
+    dirs = fan_subsample(rank, world, stride, n_total)
     res, steps, seconds = d.trace(np.repeat(pos, len(dirs), 0), dirs,
                                   H.rule(ALTITUDE_MAX, max_steps=MAX_STEPS), threads=cores)
     return res, steps, seconds, len(dirs)
@@ -149,10 +149,10 @@ def run_reference(args):
     n_total = args.rays
     stride = max(1, n_total // args.ref_rays)
     for _ in range(max(args.warmup, 0)):
-        cpu_trace(d, H, 0, stride * 8, n_total, cores)
+        cpu_trace(d, H, 0, args.gpus, stride * 8, n_total, cores)
     t_all, rays_all, steps_all = 0., 0, 0
     for _ in range(args.steps):
-        _, steps, seconds, n = cpu_trace(d, H, 0, stride, n_total, cores)
+        _, steps, seconds, n = cpu_trace(d, H, 0, args.gpus, stride, n_total, cores)
         t_all += seconds
         rays_all += n
         steps_all += steps
@@ -235,9 +235,8 @@ def main():
 
     # ---- rays of this rank (pinned host copies for the e2e leg) -------------------------
     n = args.rays
-    lat, lon, dirs = fan(rank, 0, n) if n == N_AZ * N_EL else (
-        DET_LAT + 0.01 * rank, DET_LON + 0.01 * rank,
-        fan_subsample(rank, (N_AZ * N_EL) // n, N_AZ * N_EL)[:n])
+    lat, lon, dirs = fan(rank, world, 0, n) if n == N_AZ * N_EL else (
+        DET_LAT, DET_LON, fan_subsample(rank, world, (N_AZ * N_EL) // n, N_AZ * N_EL)[:n])
     origin, data_index = stepper.position(lat, lon, DET_HEIGHT, 0)
     assert data_index == 0
     h_pos = torch.empty((n, 3), dtype=torch.float64, pin_memory=True)
@@ -300,6 +299,13 @@ def main():
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / args.steps
     launches += args.steps
+    rank_ms = torch.tensor([kernel_ms], device=dev, dtype=torch.float64)
+    all_ms = [torch.zeros_like(rank_ms) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(all_ms, rank_ms)
+    else:
+        all_ms = [rank_ms]
+    per_rank_kernel_ms = [round(float(t.item()), 3) for t in all_ms]
 
     # ---- end to end through the host-pointer C ABI call -------------------------------------
     e2e = None
@@ -362,7 +368,7 @@ def main():
         d, H, kind = reference_driver()
         cores = os.cpu_count() or 1
         stride = max(1, (N_AZ * N_EL) // args.cpu_rays)
-        ref, ref_steps, seconds, m = cpu_trace(d, H, 0, stride, N_AZ * N_EL, cores)
+        ref, ref_steps, seconds, m = cpu_trace(d, H, 0, world, stride, N_AZ * N_EL, cores)
         cpu = {"value": m / seconds / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
                "ns_per_step": 1e9 * seconds / max(ref_steps, 1), "seconds": seconds,
                "sample": "every %d-th ray of the rank-0 fan (%d rays)" % (stride, m)}
@@ -384,6 +390,7 @@ def main():
         "data": "synthetic", "config": workload_config(n, world),
         "ns_per_step": kernel_ms * 1e6 / max(steps, 1),
         "steps_per_ray": steps / n, "samples_per_step": samples / max(steps, 1),
+        "per_rank_kernel_ms": per_rank_kernel_ms,
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,
         "cpu_baseline": cpu, "plan_bytes": plan.bytes,
     }

@@ -113,6 +113,11 @@ TURTLE_API void turtle_plan_counters_sync(struct turtle_plan * plan);
 /* Tuning: CTAs per SM and threads per CTA of the persistent kernels (0 = default). */
 TURTLE_API void turtle_plan_launch_set(
     struct turtle_plan * plan, int ctas_per_sm, int threads);
+/* Ray scheduling of the trace calls. 0: rays are started in the caller's order.
+ * 1: longest-expected-first -- rays are started by increasing |sin(elevation)| of their
+ * direction (grazing rays take the most steps; a long ray that starts last bounds the
+ * kernel time). Results do not depend on the mode, only the time does. */
+TURTLE_API void turtle_plan_schedule_set(struct turtle_plan * plan, int mode);
 
 /* ---- whole rays: reset, query, then step until the rule stops the ray ------ */
 TURTLE_API enum turtle_return turtle_stepper_trace_batch(

@@ -152,6 +152,10 @@ def test_determinism_and_chunking(small_stack):
     plan.launch_set(2, 64)  # another grid: same answers
     c = plan.trace(pos, dirs, rule)
     assert a.tobytes() == c.tobytes()
+    plan.schedule_set(1)    # longest-expected-first queue order: same answers
+    c = plan.trace(pos, dirs, rule)
+    assert a.tobytes() == c.tobytes()
+    plan.schedule_set(0)
     d_res = torch.empty((n, 96), dtype=torch.uint8, device="cuda:0")
     plan.trace_device(n, torch.from_numpy(pos).cuda(), torch.from_numpy(dirs).cuda(), rule, d_res)
     torch.cuda.synchronize()

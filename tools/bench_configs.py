@@ -51,6 +51,7 @@ def timed(fn, steps, warmup=3):
 def trace_config(name, scene, pos, dirs, rule_o, rule_g, args, ops_per_sample, note):
     stepper, maps, stacks = scene.product()
     plan = stepper.freeze(0)
+    plan.schedule_set(args.schedule)
     n = len(pos)
     d_pos, d_dir = torch.from_numpy(pos).to(DEV), torch.from_numpy(dirs).to(DEV)
     d_res = torch.empty((n, 96), dtype=torch.uint8, device=DEV)
@@ -66,7 +67,7 @@ def trace_config(name, scene, pos, dirs, rule_o, rule_g, args, ops_per_sample, n
     dfma = tb.dfma_peak(3)
     achieved = ops_per_sample * c["samples"] / (ms * 1e-3) / 1e12
     line = {
-        "config": name, "workload": note, "rays": n, "ms_per_step": ms,
+        "config": name, "workload": note, "rays": n, "schedule": args.schedule, "ms_per_step": ms,
         "Mrays_per_s": n / ms / 1e3, "ns_per_step": ms * 1e6 / max(c["steps"], 1),
         "steps_per_ray": c["steps"] / n, "samples_per_step": c["samples"] / max(c["steps"], 1),
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": dfma / 1e3,
@@ -314,6 +315,7 @@ def main():
     ap.add_argument("--walk", type=int, default=100)
     ap.add_argument("--cpu-rays", type=int, default=1 << 18)
     ap.add_argument("--map-nodes", type=int, default=20000)
+    ap.add_argument("--schedule", type=int, default=0)
     args = ap.parse_args()
     if args.config == "c1" and args.range is None:
         args.range = 0.

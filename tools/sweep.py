@@ -16,7 +16,7 @@ def main():
     plan = stepper.freeze(0)
     rule = tb.trace_rule(B.ALTITUDE_MAX, max_steps=B.MAX_STEPS)
     n = B.N_AZ * B.N_EL
-    lat, lon, dirs = B.fan(0, 0, n)
+    lat, lon, dirs = B.fan(0, 1, 0, n)
     if order == "az":  # azimuth-major instead of the bench's elevation-major order
         dirs = dirs.reshape(B.N_EL, B.N_AZ, 3).transpose(1, 0, 2).reshape(n, 3).copy()
     origin, _ = stepper.position(lat, lon, B.DET_HEIGHT, 0)
@@ -26,9 +26,10 @@ def main():
     d_pos, d_dir = h_pos.cuda(), h_dir.cuda()
     d_res = torch.empty((n, 96), dtype=torch.uint8, device="cuda")
     res_np = h_res.numpy().view(tb.TRACE_RESULT).reshape(n)
-    configs = [(4, 128), (5, 128), (6, 128), (8, 128), (16, 32), (24, 32), (32, 32)]
-    for (c, t) in configs:
+    configs = [(5, 128, 0), (6, 128, 0), (6, 128, 1), (8, 128, 0)]
+    for (c, t, sched) in configs:
         plan.launch_set(c, t)
+        plan.schedule_set(sched)
         for _ in range(2):
             plan.trace_device(n, d_pos, d_dir, rule, d_res)
         torch.cuda.synchronize()
@@ -44,7 +45,7 @@ def main():
             plan.trace(h_pos.numpy(), h_dir.numpy(), rule, results=res_np)
         host_ms = (time.perf_counter() - t0) / 2 * 1e3
         c2 = plan.counters()
-        print(json.dumps(dict(order=order, ctas_per_sm=c, threads=t, device_ms=round(ms, 2), mrays=round(n / ms / 1e3, 2),
+        print(json.dumps(dict(order=order, schedule=sched, ctas_per_sm=c, threads=t, device_ms=round(ms, 2), mrays=round(n / ms / 1e3, 2),
                               host_ms=round(host_ms, 2), host_mrays=round(n / host_ms / 1e3, 2),
                               host_kernel_ms_sum=round(c2["kernel_ms"], 1))), flush=True)
 

@@ -107,6 +107,7 @@ SIGNATURES = {
     "turtle_plan_counters_get": (None, [_P, C.POINTER(PlanCounters)]),
     "turtle_plan_counters_sync": (None, [_P]),
     "turtle_plan_launch_set": (None, [_P, _I, _I]),
+    "turtle_plan_schedule_set": (None, [_P, _I]),
     # rays
     "turtle_stepper_trace_batch": (_I, [_P, _N, _P, _P, C.POINTER(TraceRule), _P]),
     "turtle_stepper_trace_batch_device": (_I, [_P, _N, _P, _P, C.POINTER(TraceRule), _P, _P]),

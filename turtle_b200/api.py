@@ -316,6 +316,9 @@ class Plan:
     def launch_set(self, ctas_per_sm=0, threads=0):
         lib.turtle_plan_launch_set(self._p, ctas_per_sm, threads)
 
+    def schedule_set(self, mode):
+        lib.turtle_plan_schedule_set(self._p, mode)
+
     def counters(self, sync=False):
         if sync:
             lib.turtle_plan_counters_sync(self._p)

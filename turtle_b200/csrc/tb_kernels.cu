@@ -21,6 +21,7 @@
  * No tensor cores: the path is FP64-pipe / issue bound (DESIGN.md roofline).
  */
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <stdio.h>
 #include <string.h>
@@ -56,6 +57,7 @@ enum { MODE_IDLE = 0, MODE_INIT = 1, MODE_TENT = 2, MODE_BISECT = 3 };
 
 struct TraceArgs {
         unsigned long long n;
+        const unsigned * order; /* queue position -> ray index, or NULL (identity) */
         const double * position;
         const double * direction;
         turtle_trace_result * results;
@@ -114,8 +116,10 @@ __global__ void __launch_bounds__(128, MINB)
                                 base = __shfl_sync(FULL, base, 0);
                                 if (mode == MODE_IDLE) {
                                         const unsigned rank = __popc(idle & ((1u << lane) - 1u));
-                                        const unsigned long long r = base + rank;
-                                        if (r < A.n) {
+                                        const unsigned long long q = base + rank;
+                                        if (q < A.n) {
+                                                const unsigned long long r =
+                                                    (A.order != NULL) ? A.order[q] : q;
                                                 const double * p = A.position + 3ull * r;
                                                 const double * d = A.direction + 3ull * r;
                                                 const double pos[3] = { p[0], p[1], p[2] };
@@ -334,6 +338,31 @@ __global__ void __launch_bounds__(128, MINB)
         if (lane == 0u) {
                 atomicAdd(A.cursor + 1, steps64);
                 atomicAdd(A.cursor + 2, samples64);
+        }
+}
+
+/* Longest-expected-first scheduling: the number of steps of a ray grows as it runs
+ * closer to the horizontal (it stays near the ground), and the kernel time is bounded
+ * below by the LATEST-starting long ray. Key = |sin(elevation)| w.r.t. the geocentric
+ * vertical at the origin; rays are handed out by increasing key. */
+__global__ void schedule_key_kernel(unsigned long long n, const double * __restrict__ position,
+    const double * __restrict__ direction, unsigned * __restrict__ keys,
+    unsigned * __restrict__ index)
+{
+        const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+             i < n; i += stride) {
+                const double px = position[3 * i], py = position[3 * i + 1], pz = position[3 * i + 2];
+                const double dx = direction[3 * i], dy = direction[3 * i + 1], dz = direction[3 * i + 2];
+                const double pp = px * px + py * py + pz * pz;
+                const double dd = dx * dx + dy * dy + dz * dz;
+                float k = 1.f;
+                if ((pp > 0.) && (dd > 0.))
+                        k = (float)(fabs(px * dx + py * dy + pz * dz) * rsqrt(pp * dd));
+                if (!(k >= 0.f)) k = 1.f; /* NaN: the kernel flags the ray anyway */
+                if (k > 1.f) k = 1.f;
+                keys[i] = __float_as_uint(k); /* non negative floats sort as integers */
+                index[i] = (unsigned)i;
         }
 }
 
@@ -633,6 +662,11 @@ struct turtle_plan {
         std::vector<struct turtle_stack *> pinned;
         unsigned long long * d_counters; /* N_SLOTS + 1 triplets */
         turtle_plan_counters counters;
+        /* ray scheduling (turtle_plan_schedule_set) */
+        int schedule;
+        unsigned * d_sched[4]; /* per pipeline slot: keys, index, keys', order */
+        void * d_sched_tmp[4];
+        size_t sched_rays[4], sched_tmp_bytes[4];
         /* host-pointer pipeline */
         cudaStream_t stream[N_SLOTS];
         cudaEvent_t ev0[N_SLOTS], ev1[N_SLOTS];
@@ -733,6 +767,13 @@ extern "C" enum turtle_return turtle_stepper_freeze(
         plan->d_maps = NULL;
         plan->d_tiles = NULL;
         plan->d_counters = NULL;
+        plan->schedule = 0;
+        for (int s = 0; s < 4; s++) {
+                plan->d_sched[s] = NULL;
+                plan->d_sched_tmp[s] = NULL;
+                plan->sched_rays[s] = 0;
+                plan->sched_tmp_bytes[s] = 0;
+        }
         plan->slot_rays = 0;
         for (int s = 0; s < N_SLOTS; s++) {
                 plan->stream[s] = NULL;
@@ -828,6 +869,10 @@ extern "C" void turtle_plan_destroy(struct turtle_plan ** plan_)
                 cudaFree(plan->d_in[s]);
                 cudaFree(plan->d_out[s]);
         }
+        for (int s = 0; s < 4; s++) {
+                cudaFree(plan->d_sched[s]);
+                cudaFree(plan->d_sched_tmp[s]);
+        }
         cudaFree(plan->pool);
         cudaFree(plan->d_maps);
         cudaFree(plan->d_tiles);
@@ -849,6 +894,53 @@ extern "C" void turtle_plan_launch_set(struct turtle_plan * plan, int ctas_per_s
 {
         plan->ctas_per_sm = ctas_per_sm;
         plan->threads = threads;
+}
+
+extern "C" void turtle_plan_schedule_set(struct turtle_plan * plan, int mode)
+{
+        plan->schedule = mode;
+}
+
+/* Build the queue order of a launch (longest-expected-first) in plan->d_sched. */
+static cudaError_t schedule_rays(struct turtle_plan * plan, int slot, size_t n,
+    const double * d_position, const double * d_direction, cudaStream_t stream,
+    const unsigned ** order)
+{
+        *order = NULL;
+        if ((plan->schedule == 0) || (n < 2) || (n > 0x7fffffffull)) return cudaSuccess;
+        cudaError_t err = cudaSuccess;
+        if (plan->sched_rays[slot] < n) {
+                cudaFree(plan->d_sched[slot]);
+                cudaFree(plan->d_sched_tmp[slot]);
+                plan->d_sched[slot] = NULL;
+                plan->d_sched_tmp[slot] = NULL;
+                plan->sched_rays[slot] = 0;
+                size_t tmp = 0;
+                err = cub::DeviceRadixSort::SortPairs(NULL, tmp, (const unsigned *)NULL,
+                    (unsigned *)NULL, (const unsigned *)NULL, (unsigned *)NULL, (int)n, 0, 31,
+                    stream);
+                if (err == cudaSuccess)
+                        err = cudaMalloc((void **)&plan->d_sched[slot], 4 * n * sizeof(unsigned));
+                if (err == cudaSuccess) err = cudaMalloc(&plan->d_sched_tmp[slot], tmp);
+                if (err != cudaSuccess) return err;
+                plan->sched_rays[slot] = n;
+                plan->sched_tmp_bytes[slot] = tmp;
+        }
+        unsigned * keys = plan->d_sched[slot];
+        unsigned * index = keys + plan->sched_rays[slot];
+        unsigned * keys_out = index + plan->sched_rays[slot];
+        unsigned * sorted = keys_out + plan->sched_rays[slot];
+        const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)plan->sm_count * 16);
+        schedule_key_kernel<<<blocks, 256, 0, stream>>>(n, d_position, d_direction, keys, index);
+        plan->counters.launches++;
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+        size_t tmp = plan->sched_tmp_bytes[slot];
+        err = cub::DeviceRadixSort::SortPairs(plan->d_sched_tmp[slot], tmp, keys, keys_out, index, sorted,
+            (int)n, 0, 31, stream);
+        plan->counters.launches += 4; /* radix sort passes (library kernels) */
+        *order = sorted;
+        return err;
 }
 
 /* Grid of the persistent kernel: a multiple of the SM count. */
@@ -873,15 +965,17 @@ static enum turtle_return check_rule(turtle_function_t * fn, const struct turtle
         return TURTLE_RETURN_SUCCESS;
 }
 
-static cudaError_t launch_trace(struct turtle_plan * plan, size_t n, const double * d_position,
-    const double * d_direction, const struct turtle_trace_rule * rule,
-    struct turtle_trace_result * d_results, unsigned long long * d_counters,
-    cudaStream_t stream)
+static cudaError_t launch_trace(struct turtle_plan * plan, int slot, size_t n,
+    const double * d_position, const double * d_direction,
+    const struct turtle_trace_rule * rule, struct turtle_trace_result * d_results,
+    unsigned long long * d_counters, cudaStream_t stream)
 {
         cudaError_t err = cudaMemsetAsync(d_counters, 0x0, 4 * sizeof(unsigned long long), stream);
         if (err != cudaSuccess) return err;
         TraceArgs A;
         A.n = n;
+        err = schedule_rays(plan, slot, n, d_position, d_direction, stream, &A.order);
+        if (err != cudaSuccess) return err;
         A.position = d_position;
         A.direction = d_direction;
         A.results = d_results;
@@ -934,7 +1028,7 @@ extern "C" enum turtle_return turtle_stepper_trace_batch_device(
         memset(&plan->counters, 0x0, sizeof(plan->counters));
         plan->counters.rays = n;
         CUDA_TRY(&turtle_stepper_trace_batch_device,
-            launch_trace(plan, n, position, direction, rule, results,
+            launch_trace(plan, N_SLOTS, n, position, direction, rule, results,
                 plan->d_counters + 4 * N_SLOTS, (cudaStream_t)stream));
         return TURTLE_RETURN_SUCCESS;
 }
@@ -1026,7 +1120,7 @@ extern "C" enum turtle_return turtle_stepper_trace_batch(
                         cudaMemcpyHostToDevice, st));
                 CUDA_TRY(&turtle_stepper_trace_batch, cudaEventRecord(plan->ev0[s], st));
                 CUDA_TRY(&turtle_stepper_trace_batch,
-                    launch_trace(plan, m, d_pos, d_dir, rule, plan->d_out[s],
+                    launch_trace(plan, s, m, d_pos, d_dir, rule, plan->d_out[s],
                         plan->d_counters + 4 * s, st));
                 CUDA_TRY(&turtle_stepper_trace_batch, cudaEventRecord(plan->ev1[s], st));
                 CUDA_TRY(&turtle_stepper_trace_batch,
