@@ -219,6 +219,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner on stdout: keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/turtle_b200_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- geometry: rank 0 writes the tiles once, every rank freezes its own copy ------
@@ -394,7 +396,8 @@ def main():
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,
         "cpu_baseline": cpu, "plan_bytes": plan.bytes,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
