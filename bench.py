@@ -2,7 +2,7 @@
 """bench.py -- Mrays/s of the batched DEM ray stepper on B200 (BASELINE.json metric).
 
 Workload (BASELINE.json configs[1], SURVEY.md section 8d "C2"): a muography fan of
-4096 x 4096 = 16 Mi rays (elevation-major order, lowest elevation first:
+4096 x 4096 = 16 Mi rays (lowest elevations first, in azimuth-coherent bundles of 32:
 turtle_b200.synth.fan_angles) from a detector at (46.5 N, 3.5 E) + 1 m through a synthetic
 SRTMGL1-shaped 3 x 3 stack of 3601 x 3601 one-arc-second tiles, geodetic coordinates,
 range 0 (no local approximation), slope 0.4, resolution 1e-2. A ray stops when it
@@ -44,10 +44,15 @@ DET_LAT, DET_LON, DET_HEIGHT = 46.5, 3.5, 1.0
 STACK_LAT0, STACK_LON0, STACK_N = 45, 2, 3
 ALTITUDE_MAX, MAX_STEPS = 9000.0, 100000
 N_AZ = N_EL = 4096
-# FP64-pipe instructions (DFMA/DMUL/DADD/DSETP, FMA = 1) per geodetic-stack sample: 382
-# measured with ncu (profiles/r01_trace_kernel_ncu_full.md: sm__inst_executed_pipe_fp64 /
-# samples); the static estimate of SURVEY.md App. C is 480 (it counts both branches).
+# ALGORITHMIC FP64-pipe instructions (DFMA/DMUL/DADD/DSETP, FMA = 1) per geodetic-stack
+# sample = 382: the dynamic count of the straightforward expansion of the reference's
+# expressions (IEEE divisions, sqrt, library asin/atan2), measured with ncu on the first
+# kernel of this round (profiles/r01_trace_kernel_ncu_full.md). SURVEY.md App. C's static
+# estimate is 480 (it counts both asin/acos branches). The current kernel EXECUTES 264 per
+# sample (shared reciprocals, own asin/atan2: profiles/r01c_trace_kernel_ncu_full.md), so
+# its measured FP64-pipe utilisation (ncu: 47 %) is lower than the algorithmic fraction.
 OPS_PER_SAMPLE = 382.0
+EXECUTED_OPS_PER_SAMPLE = 264.0
 BYTES_PER_RAY = 48 + 96  # position + direction in, result record out
 BYTES_PER_SAMPLE = 8     # four 16-bit nodes
 
@@ -176,7 +181,7 @@ def run_reference(args):
 
 def workload_config(n_rays, gpus):
     return {"workload": "C2: %d-ray muography fan per GPU (4096 az x 4096 el, el 0.5-30 deg, "
-                        "elevation-major ray order) from "
+                        "lowest elevations first in 32-ray azimuth bundles) from "
                         "(46.5N, 3.5E)+1 m through a synthetic SRTMGL1-shaped 3x3 stack of "
                         "3601x3601 int16 tiles (233 MB), geodetic, range 0, slope 0.4, "
                         "resolution 1e-2; stop: leaves stack | alt > 9000 m | 1e5 steps" % n_rays,
@@ -358,6 +363,9 @@ def main():
         "peak_source": "turtle_b200_dfma_peak() measured in this run (MEASURED_PEAKS.json has "
                        "no FP64 entry)",
         "ops_per_sample": OPS_PER_SAMPLE, "samples_per_launch": samples,
+        "executed_ops_per_sample": EXECUTED_OPS_PER_SAMPLE,
+        "fp64_pipe_utilisation": EXECUTED_OPS_PER_SAMPLE * samples / (kernel_ms * 1e-3) / 1e12 /
+        (dfma / 1e3) if dfma > 0 else None,
         "kernel_ms": kernel_ms, "traffic": None,
         "hbm": {"achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak,
                 "unit": "GB/s", "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,

@@ -16,8 +16,11 @@ def main():
     plan = stepper.freeze(0)
     rule = tb.trace_rule(B.ALTITUDE_MAX, max_steps=B.MAX_STEPS)
     n = B.N_AZ * B.N_EL
-    lat, lon, dirs = B.fan(0, 1, 0, n)
-    if order == "az":  # azimuth-major instead of the bench's elevation-major order
+    from turtle_b200 import synth
+    bundle = {"el": 1, "band": 32, "band8": 8, "band128": 128}.get(order, 1)
+    lat, lon = B.DET_LAT, B.DET_LON
+    dirs = synth.fan_directions(lat, lon, B.N_AZ, B.N_EL, bundle=bundle)
+    if order == "az":  # azimuth-major
         dirs = dirs.reshape(B.N_EL, B.N_AZ, 3).transpose(1, 0, 2).reshape(n, 3).copy()
     origin, _ = stepper.position(lat, lon, B.DET_HEIGHT, 0)
     h_pos = torch.empty((n, 3), dtype=torch.float64, pin_memory=True); h_pos.numpy()[:] = origin
@@ -26,7 +29,7 @@ def main():
     d_pos, d_dir = h_pos.cuda(), h_dir.cuda()
     d_res = torch.empty((n, 96), dtype=torch.uint8, device="cuda")
     res_np = h_res.numpy().view(tb.TRACE_RESULT).reshape(n)
-    configs = [(5, 128, 0), (6, 128, 0), (6, 128, 1), (8, 128, 0)]
+    configs = [(5, 128, 0), (6, 128, 0), (8, 128, 0)]
     for (c, t, sched) in configs:
         plan.launch_set(c, t)
         plan.schedule_set(sched)

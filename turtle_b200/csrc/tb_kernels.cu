@@ -386,49 +386,254 @@ struct StepArgs {
         unsigned long long * counters; /* [1] steps */
 };
 
-/* One turtle_stepper_step per particle (ref: stepper.c:780-875). */
-template <bool LLA>
-__global__ void __launch_bounds__(128)
-    step_kernel(const __grid_constant__ tb::Geometry G, const StepArgs A)
+/* One turtle_stepper_step per particle (ref: stepper.c:780-875), with the SAME
+ * sample-granular scheduling as the trace kernel: persistent lanes pull particles from
+ * a queue; every loop iteration evaluates one stepper_sample per lane (start sample
+ * unless the particle's cached last sample is at its position, tentative end, bisection
+ * mid-points); a particle that is done writes its outputs and state and its lane is
+ * refilled. Step-granular lockstep (one thread = one whole step) would make every warp
+ * pay the 23-sample bisection of its unluckiest lane on most steps. */
+template <bool LLA, bool PROJ>
+__global__ void __launch_bounds__(128, 5)
+    walk_kernel(const __grid_constant__ tb::Geometry G, const StepArgs A)
 {
-        const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-             i < A.n; i += stride) {
-                ParticleState local;
-                ParticleState * ps = &local;
-                if (A.states != NULL)
-                        ps = A.states + i;
-                else
-                        tb::state_reset(local.st, local.lla, G.n_transforms);
-                double pos[3] = { A.position[3 * i], A.position[3 * i + 1],
-                        A.position[3 * i + 2] };
-                double dir[3] = { 0., 0., 0. };
-                const double * d = NULL;
+        __shared__ LaneStore store;
+        const unsigned tid = threadIdx.x;
+        const unsigned lane = tid & 31u;
+        const unsigned FULL = 0xffffffffu;
+#define SF(k) store.f[k][tid]
+#define SI(k) store.i[k][tid]
+
+        int mode = MODE_IDLE;
+        tb::LlaState lla[LLA ? tb::MAX_TRANSFORMS : 1];
+        unsigned my_steps = 0u, my_samples = 0u;
+        bool exhausted = false;
+
+        for (;;) {
+                bool started = false; /* the start sample is available in the lane store */
+                bool finish = false;
+                double step_out = 0.;
+                const unsigned idle = __ballot_sync(FULL, mode == MODE_IDLE);
+                if (idle != 0u) {
+                        if (!exhausted) {
+                                const int need = __popc(idle);
+                                unsigned long long base = 0ull;
+                                if (lane == 0u)
+                                        base = atomicAdd(A.counters, (unsigned long long)need);
+                                base = __shfl_sync(FULL, base, 0);
+                                if (mode == MODE_IDLE) {
+                                        const unsigned long long r =
+                                            base + __popc(idle & ((1u << lane) - 1u));
+                                        if (r < A.n) {
+                                                SI(I_RAYLO) = (int)(unsigned)(r & 0xffffffffull);
+                                                SI(I_RAYHI) = (int)(unsigned)(r >> 32);
+                                                const double pos[3] = { A.position[3 * r],
+                                                        A.position[3 * r + 1], A.position[3 * r + 2] };
+                                                SF(F_POS) = pos[0];
+                                                SF(F_POS + 1) = pos[1];
+                                                SF(F_POS + 2) = pos[2];
+                                                if (A.direction != NULL) {
+                                                        SF(F_DIR) = A.direction[3 * r];
+                                                        SF(F_DIR + 1) = A.direction[3 * r + 1];
+                                                        SF(F_DIR + 2) = A.direction[3 * r + 2];
+                                                }
+                                                double lp[3] = { DBL_MAX, DBL_MAX, DBL_MAX };
+                                                if (A.states != NULL) {
+                                                        const ParticleState * ps = A.states + r;
+                                                        lp[0] = ps->st.last_position[0];
+                                                        lp[1] = ps->st.last_position[1];
+                                                        lp[2] = ps->st.last_position[2];
+                                                        if (LLA)
+                                                                for (int t = 0; t < G.n_transforms; t++)
+                                                                        lla[t] = ps->lla[t];
+                                                } else if (LLA) {
+                                                        tb::lla_reset(lla, G.n_transforms);
+                                                }
+                                                SF(F_LASTPOS) = lp[0];
+                                                SF(F_LASTPOS + 1) = lp[1];
+                                                SF(F_LASTPOS + 2) = lp[2];
+                                                mode = MODE_INIT;
+                                                /* stepper.c:708-710: exact cache test */
+                                                if ((pos[0] == lp[0]) && (pos[1] == lp[1]) &&
+                                                    (pos[2] == lp[2])) {
+                                                        const tb::Sample & c = A.states[r].st.last;
+                                                        SF(F_LAT) = c.lat;
+                                                        SF(F_LON) = c.lon;
+                                                        SF(F_ALT) = c.alt;
+                                                        SF(F_ELEV0) = c.elev0;
+                                                        SF(F_ELEV1) = c.elev1;
+                                                        SI(I_IDX0) = c.idx0;
+                                                        SI(I_IDX1) = c.idx1;
+                                                        started = true;
+                                                }
+                                        }
+                                }
+                                if (base + (unsigned long long)need >= A.n) exhausted = true;
+                        }
+                        if (__all_sync(FULL, mode == MODE_IDLE)) {
+                                if (exhausted) break;
+                                continue;
+                        }
+                }
+                if (mode == MODE_IDLE) continue;
+
+                if (!started) {
+                        /* ---- one geometry sample ------------------------------------ */
+                        tb::Sample S;
+                        {
+                                double step = 0.;
+                                if (mode == MODE_TENT)
+                                        step = SF(F_DS);
+                                else if (mode == MODE_BISECT)
+                                        step = 0.5 * (SF(F_DS0) + SF(F_DS1));
+                                double p[3] = { SF(F_POS), SF(F_POS + 1), SF(F_POS + 2) };
+                                if (mode != MODE_INIT) {
+                                        p[0] += SF(F_DIR) * step;
+                                        p[1] += SF(F_DIR + 1) * step;
+                                        p[2] += SF(F_DIR + 2) * step;
+                                }
+                                double last_pos[3] = { SF(F_LASTPOS), SF(F_LASTPOS + 1),
+                                        SF(F_LASTPOS + 2) };
+                                tb::sample_geometry<LLA, PROJ>(
+                                    G, lla, last_pos, mode != MODE_BISECT, p, S);
+                                if (mode != MODE_BISECT) {
+                                        SF(F_LASTPOS) = last_pos[0];
+                                        SF(F_LASTPOS + 1) = last_pos[1];
+                                        SF(F_LASTPOS + 2) = last_pos[2];
+                                }
+                        }
+                        compiler_fence();
+                        my_samples++;
+
+                        bool publish = false;
+                        const int medium0 = SI(I_MEDIUM0);
+                        double ds = SF(F_DS);
+                        if (mode == MODE_INIT) {
+                                publish = true;
+                                started = true;
+                        } else if (mode == MODE_TENT) {
+                                SF(F_POS) += SF(F_DIR) * ds;
+                                SF(F_POS + 1) += SF(F_DIR + 1) * ds;
+                                SF(F_POS + 2) += SF(F_DIR + 2) * ds;
+                                publish = true;
+                                if (S.idx0 != medium0) {
+                                        SF(F_DS0) = -ds;
+                                        SF(F_DS1) = 0.;
+                                        mode = MODE_BISECT;
+                                        finish = !(0. - (-ds) > 1E-08);
+                                } else {
+                                        finish = true;
+                                }
+                                step_out = ds;
+                        } else {
+                                double ds0 = SF(F_DS0), ds1 = SF(F_DS1);
+                                const double ds2 = 0.5 * (ds0 + ds1);
+                                if (S.idx0 == medium0) {
+                                        ds0 = ds2;
+                                        SF(F_DS0) = ds0;
+                                } else {
+                                        ds1 = ds2;
+                                        SF(F_DS1) = ds1;
+                                        publish = true;
+                                        SF(F_LASTPOS) = SF(F_POS) + SF(F_DIR) * ds2;
+                                        SF(F_LASTPOS + 1) = SF(F_POS + 1) + SF(F_DIR + 1) * ds2;
+                                        SF(F_LASTPOS + 2) = SF(F_POS + 2) + SF(F_DIR + 2) * ds2;
+                                }
+                                if (!(ds1 - ds0 > 1E-08)) {
+                                        ds += ds1;
+                                        SF(F_POS) += SF(F_DIR) * ds1;
+                                        SF(F_POS + 1) += SF(F_DIR + 1) * ds1;
+                                        SF(F_POS + 2) += SF(F_DIR + 2) * ds1;
+                                        finish = true;
+                                        step_out = ds;
+                                }
+                        }
+                        if (publish) {
+                                SF(F_LAT) = S.lat;
+                                SF(F_LON) = S.lon;
+                                SF(F_ALT) = S.alt;
+                                SF(F_ELEV0) = S.elev0;
+                                SF(F_ELEV1) = S.elev1;
+                                SI(I_IDX0) = S.idx0;
+                                SI(I_IDX1) = S.idx1;
+                        }
+                        if (finish) my_steps++;
+                }
+
+                if (started && (mode == MODE_INIT)) {
+                        /* the start sample is known: stepper.c:791-821 */
+                        tb::Sample last;
+                        last.lat = last.lon = 0.;
+                        last.alt = SF(F_ALT);
+                        last.elev0 = SF(F_ELEV0);
+                        last.elev1 = SF(F_ELEV1);
+                        last.idx0 = SI(I_IDX0);
+                        last.idx1 = SI(I_IDX1);
+                        if (last.idx0 < 0) {
+                                finish = true;
+                                step_out = 0.;
+                        } else {
+                                const double ds = tb::step_length(G, last);
+                                if (A.direction == NULL) {
+                                        finish = true;
+                                        step_out = ds;
+                                } else {
+                                        SI(I_MEDIUM0) = last.idx0;
+                                        SF(F_DS) = ds;
+                                        mode = MODE_TENT;
+                                }
+                        }
+                }
+                if (!finish) continue;
+
+                /* ---- outputs and state of a finished particle ---------------------- */
+                const unsigned long long r = ((unsigned long long)(unsigned)SI(I_RAYHI) << 32) |
+                    (unsigned long long)(unsigned)SI(I_RAYLO);
+                const int idx0 = SI(I_IDX0);
                 if (A.direction != NULL) {
-                        dir[0] = A.direction[3 * i];
-                        dir[1] = A.direction[3 * i + 1];
-                        dir[2] = A.direction[3 * i + 2];
-                        d = dir;
+                        A.position[3 * r] = SF(F_POS);
+                        A.position[3 * r + 1] = SF(F_POS + 1);
+                        A.position[3 * r + 2] = SF(F_POS + 2);
                 }
-                const double ds = tb::stepper_step<LLA>(G, ps->lla, ps->st, pos, d);
-                const tb::Sample & last = ps->st.last;
-                if (d != NULL) {
-                        A.position[3 * i] = pos[0];
-                        A.position[3 * i + 1] = pos[1];
-                        A.position[3 * i + 2] = pos[2];
-                }
-                if (A.latitude != NULL) A.latitude[i] = last.lat;
-                if (A.longitude != NULL) A.longitude[i] = last.lon;
-                if (A.altitude != NULL) A.altitude[i] = last.alt;
+                if (A.latitude != NULL) A.latitude[r] = SF(F_LAT);
+                if (A.longitude != NULL) A.longitude[r] = SF(F_LON);
+                if (A.altitude != NULL) A.altitude[r] = SF(F_ALT);
                 if (A.elevation != NULL) { /* stepper.c:765-772 */
-                        A.elevation[2 * i] = (last.idx0 >= 0) ? last.elev0 : 0.;
-                        A.elevation[2 * i + 1] = (last.idx0 >= 0) ? last.elev1 : 0.;
+                        A.elevation[2 * r] = (idx0 >= 0) ? SF(F_ELEV0) : 0.;
+                        A.elevation[2 * r + 1] = (idx0 >= 0) ? SF(F_ELEV1) : 0.;
                 }
-                if (A.step != NULL) A.step[i] = ds;
+                if (A.step != NULL) A.step[r] = step_out;
                 if (A.index != NULL) {
-                        A.index[2 * i] = last.idx0;
-                        A.index[2 * i + 1] = last.idx1;
+                        A.index[2 * r] = idx0;
+                        A.index[2 * r + 1] = SI(I_IDX1);
                 }
+                if (A.states != NULL) {
+                        ParticleState * ps = A.states + r;
+                        ps->st.last_position[0] = SF(F_LASTPOS);
+                        ps->st.last_position[1] = SF(F_LASTPOS + 1);
+                        ps->st.last_position[2] = SF(F_LASTPOS + 2);
+                        ps->st.last.lat = SF(F_LAT);
+                        ps->st.last.lon = SF(F_LON);
+                        ps->st.last.alt = SF(F_ALT);
+                        ps->st.last.elev0 = SF(F_ELEV0);
+                        ps->st.last.elev1 = SF(F_ELEV1);
+                        ps->st.last.idx0 = idx0;
+                        ps->st.last.idx1 = SI(I_IDX1);
+                        if (LLA)
+                                for (int t = 0; t < G.n_transforms; t++) ps->lla[t] = lla[t];
+                }
+                mode = MODE_IDLE;
+        }
+#undef SF
+#undef SI
+        unsigned long long steps64 = my_steps, samples64 = my_samples;
+        for (int o = 16; o > 0; o >>= 1) {
+                steps64 += __shfl_down_sync(FULL, steps64, o);
+                samples64 += __shfl_down_sync(FULL, samples64, o);
+        }
+        if (lane == 0u) {
+                atomicAdd(A.counters + 1, steps64);
+                atomicAdd(A.counters + 2, samples64);
         }
 }
 
@@ -1208,11 +1413,22 @@ extern "C" enum turtle_return turtle_stepper_step_batch_device(
         A.counters = plan->d_counters + 4 * N_SLOTS;
         const int threads = 128;
         const int blocks = (int)std::min<size_t>((n + threads - 1) / threads,
-            (size_t)plan->sm_count * 8);
-        if (plan->G.range > 0.)
-                step_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(plan->G, A);
+            (size_t)plan->sm_count * 5);
+        cudaStream_t st = (cudaStream_t)stream;
+        CUDA_TRY(&turtle_stepper_step_batch_device,
+            cudaMemsetAsync(A.counters, 0x0, 4 * sizeof(unsigned long long), st));
+        const bool lla = plan->G.range > 0.;
+        bool proj = false;
+        for (int t = 0; t < plan->G.n_transforms; t++)
+                if (plan->G.transforms[t].type != tb::PROJ_GEODETIC) proj = true;
+        if (lla && proj)
+                walk_kernel<true, true><<<blocks, threads, 0, st>>>(plan->G, A);
+        else if (lla)
+                walk_kernel<true, false><<<blocks, threads, 0, st>>>(plan->G, A);
+        else if (proj)
+                walk_kernel<false, true><<<blocks, threads, 0, st>>>(plan->G, A);
         else
-                step_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(plan->G, A);
+                walk_kernel<false, false><<<blocks, threads, 0, st>>>(plan->G, A);
         plan->counters.launches++;
         plan->counters.rays = n;
         plan->counters.steps = (direction != NULL) ? n : 0;

@@ -165,28 +165,34 @@ def np_from_horizontal(lat, lon, az, el):
             + np.sin(el)[..., None] * u)
 
 
-def fan_angles(r, n_az, n_el, el_min=0.5, el_max=30.0, part=0, parts=1):
-    """(azimuth, elevation) of ray index r of the muography fan of config 2. Rays are
-    ordered ELEVATION-major, lowest elevation first: r = j_el * n_az + i_az,
+def fan_angles(r, n_az, n_el, el_min=0.5, el_max=30.0, part=0, parts=1, bundle=32):
+    """(azimuth, elevation) of ray index r of the muography fan of config 2:
     az = 360 (i + (part + 1/2) / parts) / n_az, el = el_min + (el_max - el_min) (j + 1/2) / n_el.
-    Grazing rays take the most steps, so this order hands out the longest rays first
-    and neighbouring lanes walk neighbouring azimuths at the same elevation.
+
+    Ray order: elevation BANDS of `bundle` consecutive elevations, lowest band first;
+    within a band azimuth by azimuth; within an azimuth the `bundle` elevations:
+    r = (band * n_az + i) * bundle + k, j = band * bundle + k. Grazing rays take the most
+    steps, so the longest rays are handed out first, and the `bundle` = 32 rays of a
+    warp share one vertical plane: they walk the same ground track and gather the same
+    DEM nodes (bundle = 1 is plain elevation-major order).
     `part` of `parts` interleaves the azimuths of several GPUs: together the parts form
     ONE fan of parts * n_az azimuths."""
     r = np.asarray(r, dtype=np.int64)
-    j, i = r // n_az, r % n_az
+    band, rem = r // (n_az * bundle), r % (n_az * bundle)
+    i, k = rem // bundle, rem % bundle
+    j = band * bundle + k
     return (360.0 * (i + (part + 0.5) / parts) / n_az,
             el_min + (el_max - el_min) * (j + 0.5) / n_el)
 
 
 def fan_directions(lat, lon, n_az, n_el, el_min=0.5, el_max=30.0, first=0, count=None,
-                   part=0, parts=1):
+                   part=0, parts=1, bundle=32):
     """ECEF directions of rays [first, first + count) of the fan (see fan_angles)."""
     total = n_az * n_el
     if count is None:
         count = total - first
     r = np.arange(first, first + count, dtype=np.int64)
-    az, el = fan_angles(r, n_az, n_el, el_min, el_max, part, parts)
+    az, el = fan_angles(r, n_az, n_el, el_min, el_max, part, parts, bundle)
     return np_from_horizontal(np.full(count, lat), np.full(count, lon), az, el)
 
 
