@@ -9,8 +9,8 @@
  * batched, GPU-resident entry points are declared in turtle_b200.h.
  *
  * Not provided (outside the hot path, see DESIGN.md "out of scope"):
- * turtle_map_load/dump for PNG/GeoTIFF/GRD/ASC, turtle_map_gradient,
- * turtle_stack_gradient. turtle_map_load accepts `.hgt` only.
+ * turtle_map_dump and turtle_map_load for PNG/GeoTIFF/GRD/ASC. turtle_map_load
+ * accepts `.hgt` only.
  */
 #ifndef TURTLE_H
 #define TURTLE_H
@@ -94,6 +94,9 @@ TURTLE_API enum turtle_return turtle_map_node(const struct turtle_map * map,
 TURTLE_API enum turtle_return turtle_map_elevation(
     const struct turtle_map * map, double x, double y, double * elevation,
     int * inside);
+TURTLE_API enum turtle_return turtle_map_gradient(
+    const struct turtle_map * map, double x, double y, double * gx, double * gy,
+    int * inside);
 TURTLE_API const struct turtle_projection * turtle_map_projection(
     const struct turtle_map * map);
 TURTLE_API void turtle_map_meta(const struct turtle_map * map,
@@ -119,6 +122,10 @@ TURTLE_API enum turtle_return turtle_stack_load(struct turtle_stack * stack);
 TURTLE_API enum turtle_return turtle_stack_elevation(
     struct turtle_stack * stack, double latitude, double longitude,
     double * elevation, int * inside);
+
+TURTLE_API enum turtle_return turtle_stack_gradient(
+    struct turtle_stack * stack, double latitude, double longitude,
+    double * glat, double * glon, int * inside);
 
 /* ---- stack clients (ref: include/turtle.h:773-842) ------------------------ */
 TURTLE_API enum turtle_return turtle_client_create(

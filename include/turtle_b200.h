@@ -195,6 +195,16 @@ TURTLE_API enum turtle_return turtle_map_elevation_ecef_batch_device(
     double * longitude, double * altitude, double * z, int * inside,
     void * stream);
 
+/* ---- gradients (ref: turtle_map_gradient, src/turtle/map.c:280-378)
+ * Same bits as the scalar call, including its first-row behaviour (map.c:353).
+ * gx[i], gy[i] are untouched where inside[i] == 0. */
+TURTLE_API enum turtle_return turtle_map_gradient_batch(
+    struct turtle_map * map, size_t n, const double * x, const double * y,
+    double * gx, double * gy, int * inside);
+TURTLE_API enum turtle_return turtle_map_gradient_batch_device(
+    struct turtle_map * map, size_t n, const double * x, const double * y,
+    double * gx, double * gy, int * inside, void * stream);
+
 /* ---- host bulk set-up ---------------------------------------------------------*/
 /* turtle_map_fill for every node: elevation[iy * nx + ix] (ref: map.c:183-203).
  * Stops at the first node that turtle_map_fill rejects and returns its code. */

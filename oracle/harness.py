@@ -82,6 +82,8 @@ def _load_driver():
     d.td_map_elevation.argtypes = [_P, C.c_int, C.c_size_t] + [_P] * 4
     d.td_map_node.argtypes = [_P, C.c_int, C.c_size_t] + [_P] * 5
     d.td_stack_elevation.argtypes = [_P, C.c_int, C.c_size_t] + [_P] * 4
+    d.td_map_gradient.argtypes = [_P, C.c_int, C.c_size_t] + [_P] * 5
+    d.td_stack_gradient.argtypes = [_P, C.c_int, C.c_size_t] + [_P] * 5
     d.td_map_pointer.restype = _P
     d.td_map_pointer.argtypes = [_P, C.c_int]
     d.td_stack_pointer.restype = _P
@@ -250,6 +252,21 @@ class Driver:
         inside = np.zeros(len(la), dtype=np.int32)
         self.d.td_stack_elevation(self.h, stack, len(la), _p(la), _p(lo), _p(z), _p(inside))
         return z, inside
+
+    def map_gradient(self, map_, x, y, fill=0.):
+        x, y = _f8(x), _f8(y)
+        gx, gy = np.full(len(x), fill), np.full(len(x), fill)
+        inside = np.zeros(len(x), dtype=np.int32)
+        self.d.td_map_gradient(self.h, map_, len(x), _p(x), _p(y), _p(gx), _p(gy), _p(inside))
+        return gx, gy, inside
+
+    def stack_gradient(self, stack, latitude, longitude, fill=0.):
+        la, lo = _f8(latitude), _f8(longitude)
+        glat, glon = np.full(len(la), fill), np.full(len(la), fill)
+        inside = np.zeros(len(la), dtype=np.int32)
+        self.d.td_stack_gradient(self.h, stack, len(la), _p(la), _p(lo), _p(glat), _p(glon),
+                                 _p(inside))
+        return glat, glon, inside
 
     def map_pointer(self, map_):
         return C.c_void_p(self.d.td_map_pointer(self.h, map_))

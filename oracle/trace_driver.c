@@ -48,6 +48,8 @@ struct api {
         int (*map_fill)(struct turtle_map *, int, int, double);
         int (*map_node)(const struct turtle_map *, int, int, double *, double *, double *);
         int (*map_elevation)(const struct turtle_map *, double, double, double *, int *);
+        int (*map_gradient)(const struct turtle_map *, double, double, double *, double *, int *);
+        int (*stack_gradient)(struct turtle_stack *, double, double, double *, double *, int *);
         int (*stack_create)(struct turtle_stack **, const char *, int,
             turtle_stack_locker_t *, turtle_stack_locker_t *);
         void (*stack_destroy)(struct turtle_stack **);
@@ -158,6 +160,8 @@ struct td_handle * td_open(const char * path)
         LOAD(map_fill, "turtle_map_fill");
         LOAD(map_node, "turtle_map_node");
         LOAD(map_elevation, "turtle_map_elevation");
+        LOAD(map_gradient, "turtle_map_gradient");
+        LOAD(stack_gradient, "turtle_stack_gradient");
         LOAD(stack_create, "turtle_stack_create");
         LOAD(stack_destroy, "turtle_stack_destroy");
         LOAD(stack_load, "turtle_stack_load");
@@ -590,6 +594,22 @@ void td_stack_elevation(struct td_handle * h, int stack, size_t n, const double 
         for (size_t i = 0; i < n; i++)
                 h->api.stack_elevation(h->stacks[stack], latitude[i], longitude[i], z + i,
                     inside + i);
+}
+
+/* gx / gy keep their input value where the reference leaves them untouched */
+void td_map_gradient(struct td_handle * h, int map, size_t n, const double * x, const double * y,
+    double * gx, double * gy, int * inside)
+{
+        for (size_t i = 0; i < n; i++)
+                h->api.map_gradient(h->maps[map], x[i], y[i], gx + i, gy + i, inside + i);
+}
+
+void td_stack_gradient(struct td_handle * h, int stack, size_t n, const double * latitude,
+    const double * longitude, double * glat, double * glon, int * inside)
+{
+        for (size_t i = 0; i < n; i++)
+                h->api.stack_gradient(h->stacks[stack], latitude[i], longitude[i], glat + i,
+                    glon + i, inside + i);
 }
 
 /* Raw object access for tests that drive the product's batch API on the same maps. */

@@ -506,6 +506,83 @@ int turtle_map_elevation(const struct turtle_map * map, double x, double y, doub
         return OK;
 }
 
+/* map.c:280-378, first-row behaviour of :353 included (the y slope lands in *gx) */
+int turtle_map_gradient(const struct turtle_map * map, double x, double y, double * gx,
+    double * gy, int * inside)
+{
+        int out = isnan(x) || isnan(y);
+        double hx = 0., hy = 0.;
+        if (!out) {
+                hx = (x - map->x0) / map->dx;
+                hy = (y - map->y0) / map->dy;
+                out = (hx > map->nx - 1) || (hx < 0) || (hy > map->ny - 1) || (hy < 0);
+        }
+        if (out) {
+                if (inside != NULL) {
+                        *inside = 0;
+                        return OK;
+                }
+                return fail(DOMAIN_ERROR, &turtle_map_elevation, "point is outside of map");
+        }
+        int ix = (int)hx, iy = (int)hy;
+        if (ix == map->nx - 1) {
+                ix--;
+                hx = 1.;
+        } else
+                hx -= ix;
+        if (iy == map->ny - 1) {
+                iy--;
+                hy = 1.;
+        } else
+                hy -= iy;
+        const double z00 = get_z(map, ix, iy), z10 = get_z(map, ix + 1, iy);
+        const double z01 = get_z(map, ix, iy + 1), z11 = get_z(map, ix + 1, iy + 1);
+        if (hx <= 0.5) {
+                const double gx1 = (z10 - z00) * (1. - hy) + (z11 - z01) * hy;
+                if (ix == 0) {
+                        *gx = gx1 / map->dx;
+                } else {
+                        const double z_10 = get_z(map, ix - 1, iy), z_11 = get_z(map, ix - 1, iy + 1);
+                        const double gx0 = (z00 - z_10) * (1. - hy) + (z01 - z_11) * hy;
+                        const double ax = hx + 0.5;
+                        *gx = (gx0 * (1. - ax) + gx1 * ax) / map->dx;
+                }
+        } else {
+                const double gx0 = (z10 - z00) * (1. - hy) + (z11 - z01) * hy;
+                if (ix == map->nx - 2) {
+                        *gx = gx0 / map->dx;
+                } else {
+                        const double z20 = get_z(map, ix + 2, iy), z21 = get_z(map, ix + 2, iy + 1);
+                        const double gx1 = (z20 - z10) * (1. - hy) + (z21 - z11) * hy;
+                        const double ax = hx - 0.5;
+                        *gx = (gx0 * (1. - ax) + gx1 * ax) / map->dx;
+                }
+        }
+        if (hy <= 0.5) {
+                const double gy1 = (z01 - z00) * (1. - hx) + (z11 - z10) * hx;
+                if (iy == 0) {
+                        *gx = gy1 / map->dy; /* map.c:353 */
+                } else {
+                        const double z0_1 = get_z(map, ix, iy - 1), z1_1 = get_z(map, ix + 1, iy - 1);
+                        const double gy0 = (z00 - z0_1) * (1. - hx) + (z10 - z1_1) * hx;
+                        const double ay = hy + 0.5;
+                        *gy = (gy0 * (1. - ay) + gy1 * ay) / map->dy;
+                }
+        } else {
+                const double gy0 = (z01 - z00) * (1. - hx) + (z11 - z10) * hx;
+                if (iy == map->ny - 2) {
+                        *gy = gy0 / map->dy;
+                } else {
+                        const double z02 = get_z(map, ix, iy + 2), z12 = get_z(map, ix + 1, iy + 2);
+                        const double gy1 = (z02 - z01) * (1. - hx) + (z12 - z11) * hx;
+                        const double ay = hy - 0.5;
+                        *gy = (gy0 * (1. - ay) + gy1 * ay) / map->dy;
+                }
+        }
+        if (inside != NULL) *inside = 1;
+        return OK;
+}
+
 /* io/hgt.c:61-104 (file name -> grid) and :135-147 (raw read) */
 static struct turtle_map * hgt_load(const char * path, int meta_only)
 {
@@ -742,6 +819,34 @@ int turtle_stack_elevation(struct turtle_stack * s, double latitude, double long
         const struct turtle_map * owner = s->tiles[0];
         if (s->unlock != NULL) s->unlock();
         return turtle_map_elevation(owner, longitude, latitude, elevation, inside);
+}
+
+/* turtle_stack_gradient, stack.c:364-388 */
+int turtle_stack_gradient(struct turtle_stack * s, double latitude, double longitude,
+    double * glat, double * glon, int * inside)
+{
+        if (inside != NULL) *inside = 0;
+        if (s->lock != NULL) s->lock();
+        int found = 0;
+        for (int k = 0; k < s->size; k++) {
+                const struct turtle_map * m = s->tiles[k];
+                const double hx = (longitude - m->x0) / m->dx;
+                const double hy = (latitude - m->y0) / m->dy;
+                if ((hx >= 0.) && (hx < m->nx - 1) && (hy >= 0.) && (hy < m->ny - 1)) {
+                        touch(s, k);
+                        found = 1;
+                        break;
+                }
+        }
+        if (!found && !stack_load_at(s, latitude, longitude)) {
+                if (s->unlock != NULL) s->unlock();
+                *glat = *glon = 0.;
+                if (inside != NULL) return OK;
+                return fail(PATH_ERROR, &turtle_stack_elevation, "missing elevation data");
+        }
+        const struct turtle_map * owner = s->tiles[0];
+        if (s->unlock != NULL) s->unlock();
+        return turtle_map_gradient(owner, longitude, latitude, glon, glat, inside);
 }
 
 /* ====================================================================== */

@@ -119,6 +119,24 @@ def test_fused_ecef_elevation(ora):
     assert np.abs(gz[both] - wz[both]).max() < 1e-6  # x, y move by ~1e-9 m; slope < 100
 
 
+def test_map_gradient_bit_exact(ora):
+    """turtle_map_gradient_batch vs the oracle: + - * / only, so bit-exact; gy is left
+    untouched in the first row of cells as in the reference (map.c:353)."""
+    mp = utm_map(n=301)
+    m = ora.map_create(mp["nx"], mp["ny"], mp["x"], mp["y"], mp["z"], mp["projection"], mp["values"])
+    gm = tb.Map(mp["nx"], mp["ny"], mp["x"], mp["y"], mp["z"], mp["projection"], mp["values"])
+    rng = np.random.default_rng(16)
+    n = 1 << 18
+    x = rng.uniform(mp["x"][0] - 50, mp["x"][1] + 50, n)
+    y = rng.uniform(mp["y"][0] - 50, mp["y"][1] + 50, n)
+    y[:4000] = rng.uniform(mp["y"][0], mp["y"][0] + 6., 4000)
+    wx, wy, win = ora.map_gradient(m, x, y)
+    gx, gy, gin = gm.gradient_batch(x, y)
+    assert np.array_equal(win, gin)
+    assert np.array_equal(wx, gx) and np.array_equal(wy, gy)
+    assert (np.abs(gx[gin == 1]) > 0).mean() > 0.9
+
+
 def test_geoid_style_geodetic_map(ora):
     g = geoid_map()
     m = ora.map_create(g["nx"], g["ny"], g["x"], g["y"], g["z"], None, g["values"])

@@ -179,6 +179,36 @@ def test_reference_random_traces(drv, small_stack, rg, geoid):
     assert same(k0, k1) and same(p0, p1) and (k0 == -1).any()
 
 
+@needs_ref
+def test_reference_gradients(drv, small_stack):
+    """turtle_map_gradient / turtle_stack_gradient, bit-exact with the
+    reference, including the first-row behaviour of map.c:353 (y slope stored in *gx,
+    *gy left untouched)."""
+    ref = H.Driver(H.REF)
+    mp = utm_map(n=101)
+    rng = np.random.default_rng(8)
+    n = 50000
+    x = rng.uniform(mp["x"][0] - 30, mp["x"][1] + 30, n)
+    y = rng.uniform(mp["y"][0] - 30, mp["y"][1] + 30, n)
+    y[:2000] = rng.uniform(mp["y"][0], mp["y"][0] + 6., 2000)   # first row of cells
+    x[2000:2010] = [mp["x"][0], mp["x"][1]] * 5                    # closed borders
+    out = []
+    for d in (ref, drv):
+        m = d.map_create(mp["nx"], mp["ny"], mp["x"], mp["y"], mp["z"], mp["projection"],
+                         mp["values"])
+        out.append(d.map_gradient(m, x, y, fill=-7.5))
+    for a, b in zip(*out):
+        assert same(a, b)
+    gx, gy, inside = out[0]
+    first_row = (inside == 1) & (y < mp["y"][0] + 5.)
+    assert first_row.sum() > 500 and (gy[first_row] == -7.5).all()  # untouched, map.c:353
+    sr, sd = ref.stack_create(small_stack), drv.stack_create(small_stack)
+    la, lo = rng.uniform(44.9, 47.1, 20000), rng.uniform(1.9, 4.1, 20000)
+    la[:4], lo[:4] = [45., 46., 45.5, 46.], [2., 3., 3., 2.5]
+    for a, b in zip(ref.stack_gradient(sr, la, lo), drv.stack_gradient(sd, la, lo)):
+        assert same(a, b)
+
+
 # ---- 3. the reference's own closed-form assertions (tests/test-turtle.c) ------------------
 
 FLT_EPSILON = 1.1920929e-07

@@ -63,6 +63,7 @@ SIGNATURES = {
     "turtle_map_fill": (_I, [_P, _I, _I, _D]),
     "turtle_map_node": (_I, [_P, _I, _I, c_double_p, c_double_p, c_double_p]),
     "turtle_map_elevation": (_I, [_P, _D, _D, c_double_p, c_int_p]),
+    "turtle_map_gradient": (_I, [_P, _D, _D, c_double_p, c_double_p, c_int_p]),
     "turtle_map_projection": (_P, [_P]),
     "turtle_map_meta": (None, [_P, C.POINTER(MapInfo), C.POINTER(C.c_char_p)]),
     # ecef
@@ -76,6 +77,7 @@ SIGNATURES = {
     "turtle_stack_clear": (_I, [_P]),
     "turtle_stack_load": (_I, [_P]),
     "turtle_stack_elevation": (_I, [_P, _D, _D, c_double_p, c_int_p]),
+    "turtle_stack_gradient": (_I, [_P, _D, _D, c_double_p, c_double_p, c_int_p]),
     "turtle_client_create": (_I, [_PP, _P]),
     "turtle_client_destroy": (_I, [_PP]),
     "turtle_client_clear": (_I, [_P]),
@@ -130,6 +132,8 @@ SIGNATURES = {
     "turtle_map_elevation_batch_device": (_I, [_P, _N, _P, _P, _P, _P, _P]),
     "turtle_map_elevation_ecef_batch": (_I, [_P, _N, _P, _P, _P, _P, _P, _P]),
     "turtle_map_elevation_ecef_batch_device": (_I, [_P, _N, _P, _P, _P, _P, _P, _P, _P]),
+    "turtle_map_gradient_batch": (_I, [_P, _N, _P, _P, _P, _P, _P]),
+    "turtle_map_gradient_batch_device": (_I, [_P, _N, _P, _P, _P, _P, _P, _P]),
     "turtle_map_fill_batch": (_I, [_P, _P]),
     "turtle_map_fill_rows": (_I, [_P, _I, _I, _P]),
     # utilities

@@ -183,6 +183,14 @@ class Map:
                                               _ptr(inside)))
         return z, inside
 
+    def gradient_batch(self, x, y):
+        x, y = _f8(x), _f8(y)
+        gx, gy = np.zeros(len(x)), np.zeros(len(x))
+        inside = np.zeros(len(x), dtype=np.int32)
+        _check(lib.turtle_map_gradient_batch(self._p, len(x), _ptr(x), _ptr(y), _ptr(gx),
+                                             _ptr(gy), _ptr(inside)))
+        return gx, gy, inside
+
     def elevation_ecef_batch(self, ecef):
         ecef = _f8(ecef, (-1, 3))
         n = len(ecef)

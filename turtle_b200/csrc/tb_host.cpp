@@ -609,6 +609,23 @@ extern "C" enum turtle_return turtle_map_elevation(const struct turtle_map * map
         return TURTLE_RETURN_SUCCESS;
 }
 
+/* ref: turtle_map_gradient, map.c:388-393 (it registers turtle_map_elevation as the
+ * failing function, which is kept) */
+extern "C" enum turtle_return turtle_map_gradient(const struct turtle_map * map, double x,
+    double y, double * gx, double * gy, int * inside)
+{
+        const tb::MapDesc d = map_desc(map);
+        const int in = tb::map_gradient(d, x, y, *gx, *gy);
+        if (inside != NULL) {
+                *inside = in;
+                return TURTLE_RETURN_SUCCESS;
+        }
+        if (!in)
+                return RAISE(&turtle_map_elevation, TURTLE_RETURN_DOMAIN_ERROR, MAP_C,
+                    "point is outside of map");
+        return TURTLE_RETURN_SUCCESS;
+}
+
 extern "C" const struct turtle_projection * turtle_map_projection(
     const struct turtle_map * map)
 {
@@ -972,6 +989,57 @@ extern "C" enum turtle_return turtle_stack_elevation(struct turtle_stack * stack
 {
         return stack_elevation_scalar(stack, latitude, longitude, elevation, inside,
             FN(&turtle_stack_elevation));
+}
+
+/* ref: turtle_stack_gradient, stack.c:364-388. Every tile is made resident first: the
+ * answer is the one of the device rule tb::stack_gradient. */
+extern "C" enum turtle_return turtle_stack_gradient(struct turtle_stack * stack,
+    double latitude, double longitude, double * glat, double * glon, int * inside)
+{
+        if (inside != NULL) *inside = 0;
+        enum turtle_return rc = tbh::stack_load_all(stack, FN(&turtle_stack_elevation));
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        tb::Geometry G;
+        memset(&G, 0x0, sizeof(G));
+        std::vector<tb::MapDesc> maps;
+        std::vector<tb::TileRec> tiles;
+        tb::StackDesc & S = G.stacks[0];
+        S.lat0 = stack->latitude_0;
+        S.dlat = stack->latitude_delta;
+        S.lon0 = stack->longitude_0;
+        S.dlon = stack->longitude_delta;
+        S.inv_dlat = (S.dlat > 0.) ? 1. / S.dlat : 0.;
+        S.inv_dlon = (S.dlon > 0.) ? 1. / S.dlon : 0.;
+        S.nlat = stack->latitude_n;
+        S.nlon = stack->longitude_n;
+        S.nlat_d = (double)S.nlat;
+        S.nlon_d = (double)S.nlon;
+        const tb::TileRec none = { NULL, 0., 0., -1, 0 };
+        for (size_t c = 0; c < stack->tile.size(); c++) {
+                if (stack->tile[c] == NULL) {
+                        tiles.push_back(none);
+                        continue;
+                }
+                const tb::TileRec rec = { stack->tile[c]->nodes.data(), stack->tile[c]->x0,
+                        stack->tile[c]->y0, (int)maps.size(), 0 };
+                tiles.push_back(rec);
+                maps.push_back(map_desc(stack->tile[c]));
+        }
+        int in = 0;
+        if (!tiles.empty()) {
+                G.maps = maps.data();
+                G.tiles = tiles.data();
+                in = tb::stack_gradient(G, S, latitude, longitude, *glat, *glon);
+        }
+        if (!in) *glat = *glon = 0.;
+        if (inside != NULL) {
+                *inside = in;
+                return TURTLE_RETURN_SUCCESS;
+        }
+        if (!in)
+                return RAISE(&turtle_stack_elevation, TURTLE_RETURN_PATH_ERROR, STACK_C,
+                    "missing elevation data in `%s'", stack->root.c_str());
+        return TURTLE_RETURN_SUCCESS;
 }
 
 static const char * CLIENT_C = "src/turtle/client.c";
@@ -1481,6 +1549,7 @@ extern "C" const char * turtle_error_function(turtle_function_t * caller)
         NAME(turtle_map_destroy);
         NAME(turtle_map_elevation);
         NAME(turtle_map_fill);
+        NAME(turtle_map_gradient);
         NAME(turtle_map_load);
         NAME(turtle_map_meta);
         NAME(turtle_map_node);
@@ -1495,6 +1564,7 @@ extern "C" const char * turtle_error_function(turtle_function_t * caller)
         NAME(turtle_stack_create);
         NAME(turtle_stack_destroy);
         NAME(turtle_stack_elevation);
+        NAME(turtle_stack_gradient);
         NAME(turtle_stack_load);
         NAME(turtle_stepper_add_flat);
         NAME(turtle_stepper_add_layer);

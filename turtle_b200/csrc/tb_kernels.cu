@@ -761,6 +761,24 @@ __global__ void __launch_bounds__(256) map_elevation_kernel(const tb::MapDesc M,
         }
 }
 
+/* ref: turtle_map_gradient, map.c:280-378 */
+__global__ void __launch_bounds__(256) map_gradient_kernel(const tb::MapDesc M,
+    unsigned long long n, const double * __restrict__ x, const double * __restrict__ y,
+    double * __restrict__ gx, double * __restrict__ gy, int * __restrict__ inside)
+{
+        const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+             i < n; i += stride) {
+                double a = gx[i], b = gy[i];
+                const int in = tb::map_gradient(M, x[i], y[i], a, b);
+                if (in) {
+                        gx[i] = a;
+                        gy[i] = b;
+                }
+                if (inside != NULL) inside[i] = in;
+        }
+}
+
 /* ECEF -> geodetic -> (projection) -> bilinear, fused: 24 B in, up to 36 B out
  * per point, nothing intermediate in HBM. */
 __global__ void __launch_bounds__(256) map_elevation_ecef_kernel(const tb::MapDesc M,
@@ -1742,6 +1760,41 @@ extern "C" enum turtle_return turtle_map_elevation_batch(struct turtle_map * map
         return TURTLE_RETURN_SUCCESS;
 }
 
+extern "C" enum turtle_return turtle_map_gradient_batch_device(struct turtle_map * map,
+    size_t n, const double * x, const double * y, double * gx, double * gy, int * inside,
+    void * stream)
+{
+        tb::MapDesc M;
+        enum turtle_return rc = map_mirror(FN(&turtle_map_gradient_batch_device), map, &M);
+        if ((rc != TURTLE_RETURN_SUCCESS) || (n == 0)) return rc;
+        map_gradient_kernel<<<stream_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(
+            M, n, x, y, gx, gy, inside);
+        CUDA_TRY(&turtle_map_gradient_batch_device, cudaGetLastError());
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_map_gradient_batch(struct turtle_map * map, size_t n,
+    const double * x, const double * y, double * gx, double * gy, int * inside)
+{
+        enum turtle_return rc = require_current(FN(&turtle_map_gradient_batch));
+        if ((rc != TURTLE_RETURN_SUCCESS) || (n == 0)) return rc;
+        DeviceBuffers B;
+        double *d_x, *d_y, *d_gx, *d_gy;
+        int * d_in;
+        DEV_IN(&turtle_map_gradient_batch, B, d_x, x, n * sizeof(double));
+        DEV_IN(&turtle_map_gradient_batch, B, d_y, y, n * sizeof(double));
+        DEV_IN(&turtle_map_gradient_batch, B, d_gx, gx, n * sizeof(double));
+        DEV_IN(&turtle_map_gradient_batch, B, d_gy, gy, n * sizeof(double));
+        DEV_OUT(&turtle_map_gradient_batch, B, d_in, inside, n * sizeof(int));
+        rc = turtle_map_gradient_batch_device(map, n, d_x, d_y, d_gx, d_gy, d_in, NULL);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        CUDA_TRY(&turtle_map_gradient_batch, cudaDeviceSynchronize());
+        DEV_BACK(&turtle_map_gradient_batch, gx, d_gx, n * sizeof(double));
+        DEV_BACK(&turtle_map_gradient_batch, gy, d_gy, n * sizeof(double));
+        DEV_BACK(&turtle_map_gradient_batch, inside, d_in, n * sizeof(int));
+        return TURTLE_RETURN_SUCCESS;
+}
+
 extern "C" enum turtle_return turtle_map_elevation_ecef_batch_device(struct turtle_map * map,
     size_t n, const double * ecef, double * latitude, double * longitude, double * altitude,
     double * z, int * inside, void * stream)
@@ -1840,6 +1893,8 @@ extern "C" const char * tb_batch_function_name(turtle_function_t * caller)
         NAME(turtle_map_elevation_batch_device);
         NAME(turtle_map_elevation_ecef_batch);
         NAME(turtle_map_elevation_ecef_batch_device);
+        NAME(turtle_map_gradient_batch);
+        NAME(turtle_map_gradient_batch_device);
 #undef NAME
         return NULL;
 }
