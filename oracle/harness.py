@@ -108,6 +108,14 @@ class Driver:
         self._unlocked_stacks = 0
         if not self.h:
             raise OSError("could not open %s" % library)
+        if os.path.realpath(library) == os.path.realpath(PRODUCT):
+            # the driver installs its own error handler; the product library keeps ONE
+            # handler per process, so hand it back to the Python binding
+            try:
+                from turtle_b200 import api
+                api.install_handler()
+            except ImportError:
+                pass
 
     def close(self):
         if self.h:

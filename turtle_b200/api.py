@@ -34,11 +34,19 @@ def _on_error(code, function, message):
     _last_error.append((code, message.decode() if message else ""))
 
 
-lib.turtle_error_handler_set(C.cast(_on_error, C.c_void_p))
+def install_handler():
+    """(Re)install the Python error handler: it is a process-wide setting of the library
+    (turtle_error_handler_set) that other users of the same .so may have replaced."""
+    lib.turtle_error_handler_set(C.cast(_on_error, C.c_void_p))
+
+
+install_handler()
 
 
 def _check(rc):
     if rc != 0:
+        if not _last_error:
+            install_handler()  # someone replaced the handler: be loud next time at least
         code, message = _last_error.pop() if _last_error else (rc, "turtle error %d" % rc)
         del _last_error[:]
         raise TurtleError(code, message)
