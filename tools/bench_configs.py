@@ -199,7 +199,7 @@ def c4(args):
         "per-particle stepper state on the device" % (n, k, scene.range),
         "particles": n, "walk_steps": k, "ms_total": total_ms,
         "Msteps_per_s": n * k / total_ms / 1e3, "ns_per_step": total_ms * 1e6 / (n * k),
-        "state_bytes_per_particle": 976,
+        "state_bytes_per_particle": 8 * 9 + 224 * 2,
         "cpu_baseline": {"Msteps_per_s": m * k / want["seconds"] / 1e6, "cores": os.cpu_count(),
                          "ns_per_step": 1e9 * want["seconds"] / (m * k),
                          "sample": "every %d-th particle (%d particles)" % (stride, m)},

@@ -53,7 +53,8 @@ static const char * BATCH_CU = "turtle_b200/csrc/tb_kernels.cu";
 
 namespace {
 
-enum { MODE_IDLE = 0, MODE_INIT = 1, MODE_TENT = 2, MODE_BISECT = 3 };
+enum { MODE_IDLE = 0, MODE_INIT = 1, MODE_TENT = 2, MODE_BISECT = 3, MODE_REBUILD = 4,
+       MODE_FINISH = 5 };
 
 struct TraceArgs {
         unsigned long long n;
@@ -77,7 +78,8 @@ __device__ __forceinline__ bool finite3(const double v[3])
  * file to the FP64 code of the sample: no spills at 6 CTAs per SM. */
 enum { F_POS = 0, F_DIR = 3, F_LAT = 6, F_LON, F_ALT, F_ELEV0, F_ELEV1, F_DS, F_DS0, F_DS1,
        F_LEN, F_TOTAL = F_LEN + TURTLE_TRACE_MEDIA, F_LASTPOS, N_F = F_LASTPOS + 3 };
-enum { I_IDX0 = 0, I_IDX1, I_MEDIUM0, I_NSTEPS, I_NCHANGES, I_HASH, I_RAYLO, I_RAYHI, N_I };
+enum { I_IDX0 = 0, I_IDX1, I_MEDIUM0, I_NSTEPS, I_NCHANGES, I_HASH, I_RAYLO, I_RAYHI,
+       I_PEND, I_PEND_N0, I_RESUME, I_RB_AXIS, N_I };
 
 struct LaneStore {
         double f[N_F][128];
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(128, MINB)
                                                 SI(I_NCHANGES) = 0;
                                                 SI(I_RAYLO) = (int)(unsigned)(r & 0xffffffffull);
                                                 SI(I_RAYHI) = (int)(unsigned)(r >> 32);
+                                                SI(I_PEND) = 0;
                                                 mode = MODE_INIT;
                                                 /* every ray starts from a reset stepper
                                                  * (turtle_stepper_reset, stepper.c:647-651) */
@@ -173,19 +176,61 @@ __global__ void __launch_bounds__(128, MINB)
                 }
                 if (mode == MODE_IDLE) continue;
 
-                /* ---- exactly one geometry sample per lane and iteration ---- */
+                /* ---- exactly one ECEF -> geodetic transform per lane and iteration:
+                 * the one of a geometry sample, or -- local approximation on -- one of
+                 * the three finite-difference transforms of a Jacobian rebuild that the
+                 * previous sample requested (stepper.c:144-162). Running the rebuild as
+                 * iterations of its own keeps the lanes of a warp on equal work; inline
+                 * it would make every lane wait for 3 extra transforms whenever ONE lane
+                 * rebuilds. */
+                if (LLA && (SI(I_PEND) != 0) && (mode != MODE_REBUILD)) {
+                        SI(I_RESUME) = mode;
+                        SI(I_RB_AXIS) = 0;
+                        mode = MODE_REBUILD;
+                }
                 tb::Sample S;
                 {
-                        double step = 0.; /* MODE_INIT: sample the start position */
-                        if (mode == MODE_TENT) /* stepper.c:824 */
-                                step = SF(F_DS);
-                        else if (mode == MODE_BISECT) /* stepper.c:840-844 */
-                                step = 0.5 * (SF(F_DS0) + SF(F_DS1));
-                        double p[3] = { SF(F_POS), SF(F_POS + 1), SF(F_POS + 2) };
-                        if (mode != MODE_INIT) {
-                                p[0] += SF(F_DIR) * step;
-                                p[1] += SF(F_DIR + 1) * step;
-                                p[2] += SF(F_DIR + 2) * step;
+                        double p[3];
+                        int rb_t = 0, rb_axis = 0;
+                        bool heavy = true;
+                        if (LLA && (mode == MODE_REBUILD)) {
+                                rb_t = __ffs(SI(I_PEND)) - 1;
+                                rb_axis = SI(I_RB_AXIS);
+                                p[0] = lla[rb_t].ref_ecef[0];
+                                p[1] = lla[rb_t].ref_ecef[1];
+                                p[2] = lla[rb_t].ref_ecef[2];
+                                if (rb_axis == 0) p[0] += 10.;
+                                else if (rb_axis == 1) p[1] += 10.;
+                                else p[2] += 10.;
+                        } else {
+                                double step = 0.; /* MODE_INIT: sample the start position */
+                                if (mode == MODE_TENT) /* stepper.c:824 */
+                                        step = SF(F_DS);
+                                else if (mode == MODE_BISECT) /* stepper.c:840-844 */
+                                        step = 0.5 * (SF(F_DS0) + SF(F_DS1));
+                                p[0] = SF(F_POS);
+                                p[1] = SF(F_POS + 1);
+                                p[2] = SF(F_POS + 2);
+                                if (mode != MODE_INIT) {
+                                        p[0] += SF(F_DIR) * step;
+                                        p[1] += SF(F_DIR + 1) * step;
+                                        p[2] += SF(F_DIR + 2) * step;
+                                }
+                                heavy = tb::needs_geodetic<LLA>(G, lla, p);
+                        }
+                        double pre[3] = { 0., 0., 0. };
+                        if (heavy) tb::geodetic_with_geoid(G, p, pre);
+                        if (LLA && (mode == MODE_REBUILD)) {
+                                tb::rebuild_column<PROJ>(G, lla[rb_t], G.transforms[rb_t],
+                                    ((SI(I_PEND_N0) >> rb_t) & 1) ? 3 : 0, rb_axis, pre);
+                                if (rb_axis == 2) {
+                                        SI(I_PEND) &= ~(1 << rb_t);
+                                        SI(I_RB_AXIS) = 0;
+                                        if (SI(I_PEND) == 0) mode = SI(I_RESUME);
+                                } else {
+                                        SI(I_RB_AXIS) = rb_axis + 1;
+                                }
+                                continue;
                         }
                         double last_pos[3] = { 0., 0., 0. };
                         if (LLA) {
@@ -193,12 +238,17 @@ __global__ void __launch_bounds__(128, MINB)
                                 last_pos[1] = SF(F_LASTPOS + 1);
                                 last_pos[2] = SF(F_LASTPOS + 2);
                         }
-                        tb::sample_geometry<LLA, PROJ>(
-                            G, lla, last_pos, mode != MODE_BISECT, p, S);
-                        if (LLA && (mode != MODE_BISECT)) {
-                                SF(F_LASTPOS) = last_pos[0];
-                                SF(F_LASTPOS + 1) = last_pos[1];
-                                SF(F_LASTPOS + 2) = last_pos[2];
+                        tb::Pending pending = { 0u, 0u };
+                        tb::sample_geometry<LLA, PROJ, true>(G, lla, last_pos,
+                            mode != MODE_BISECT, p, S, heavy ? pre : NULL, &pending);
+                        if (LLA) {
+                                SI(I_PEND) = (int)pending.mask;
+                                SI(I_PEND_N0) = (int)pending.n0;
+                                if (mode != MODE_BISECT) {
+                                        SF(F_LASTPOS) = last_pos[0];
+                                        SF(F_LASTPOS + 1) = last_pos[1];
+                                        SF(F_LASTPOS + 2) = last_pos[2];
+                                }
                         }
                 }
                 compiler_fence(); /* keep the state loads below out of the sample code */
@@ -366,15 +416,22 @@ __global__ void schedule_key_kernel(unsigned long long n, const double * __restr
         }
 }
 
-/* Device-side particle state of turtle_stepper_step_batch. */
-struct ParticleState {
-        tb::StepperState st;
-        tb::LlaState lla[tb::MAX_TRANSFORMS];
-};
+/* Device-side particle states of turtle_stepper_step_batch.
+ * (1) The last sample: a structure of arrays of doubles, field f of particle i at
+ *     states[f * stride + i], so that the lanes of a warp (consecutive particles) read
+ *     and write whole sectors. Fields: last position (3), lat / lon / alt / elev0 /
+ *     elev1 (5), the two indices packed in one slot (1).
+ * (2) The local approximations: one tb::LlaState per particle and transform, used IN
+ *     PLACE by the core functions. A step usually only reads the reference point (one
+ *     32-byte sector) to find that it is out of range; the Jacobian is touched when it
+ *     is applied or rebuilt. */
+enum { PS_LASTPOS = 0, PS_LAT = 3, PS_LON, PS_ALT, PS_ELEV0, PS_ELEV1, PS_INDEX, PS_FIELDS };
 
 struct StepArgs {
         unsigned long long n;
-        ParticleState * states; /* or NULL */
+        double * states; /* or NULL */
+        tb::LlaState * lla_states; /* [n][n_transforms], with `states` */
+        unsigned long long stride;
         double * position;
         const double * direction; /* or NULL: query mode */
         double * latitude;
@@ -405,7 +462,8 @@ __global__ void __launch_bounds__(128, 5)
 #define SI(k) store.i[k][tid]
 
         int mode = MODE_IDLE;
-        tb::LlaState lla[LLA ? tb::MAX_TRANSFORMS : 1];
+        tb::LlaState lla_local[LLA ? tb::MAX_TRANSFORMS : 1]; /* when no states are kept */
+        tb::LlaState * lla = lla_local;
         unsigned my_steps = 0u, my_samples = 0u;
         bool exhausted = false;
 
@@ -439,31 +497,33 @@ __global__ void __launch_bounds__(128, 5)
                                                 }
                                                 double lp[3] = { DBL_MAX, DBL_MAX, DBL_MAX };
                                                 if (A.states != NULL) {
-                                                        const ParticleState * ps = A.states + r;
-                                                        lp[0] = ps->st.last_position[0];
-                                                        lp[1] = ps->st.last_position[1];
-                                                        lp[2] = ps->st.last_position[2];
+                                                        const double * ps = A.states + r;
+                                                        lp[0] = ps[(PS_LASTPOS + 0) * A.stride];
+                                                        lp[1] = ps[(PS_LASTPOS + 1) * A.stride];
+                                                        lp[2] = ps[(PS_LASTPOS + 2) * A.stride];
                                                         if (LLA)
-                                                                for (int t = 0; t < G.n_transforms; t++)
-                                                                        lla[t] = ps->lla[t];
+                                                                lla = A.lla_states +
+                                                                    r * (unsigned long long)G.n_transforms;
                                                 } else if (LLA) {
                                                         tb::lla_reset(lla, G.n_transforms);
                                                 }
                                                 SF(F_LASTPOS) = lp[0];
                                                 SF(F_LASTPOS + 1) = lp[1];
                                                 SF(F_LASTPOS + 2) = lp[2];
+                                                SI(I_PEND) = 0;
                                                 mode = MODE_INIT;
                                                 /* stepper.c:708-710: exact cache test */
                                                 if ((pos[0] == lp[0]) && (pos[1] == lp[1]) &&
                                                     (pos[2] == lp[2])) {
-                                                        const tb::Sample & c = A.states[r].st.last;
-                                                        SF(F_LAT) = c.lat;
-                                                        SF(F_LON) = c.lon;
-                                                        SF(F_ALT) = c.alt;
-                                                        SF(F_ELEV0) = c.elev0;
-                                                        SF(F_ELEV1) = c.elev1;
-                                                        SI(I_IDX0) = c.idx0;
-                                                        SI(I_IDX1) = c.idx1;
+                                                        const double * ps = A.states + r;
+                                                        SF(F_LAT) = ps[PS_LAT * A.stride];
+                                                        SF(F_LON) = ps[PS_LON * A.stride];
+                                                        SF(F_ALT) = ps[PS_ALT * A.stride];
+                                                        SF(F_ELEV0) = ps[PS_ELEV0 * A.stride];
+                                                        SF(F_ELEV1) = ps[PS_ELEV1 * A.stride];
+                                                        const double packed = ps[PS_INDEX * A.stride];
+                                                        SI(I_IDX0) = __double2loint(packed);
+                                                        SI(I_IDX1) = __double2hiint(packed);
                                                         started = true;
                                                 }
                                         }
@@ -477,25 +537,71 @@ __global__ void __launch_bounds__(128, 5)
                 }
                 if (mode == MODE_IDLE) continue;
 
-                if (!started) {
-                        /* ---- one geometry sample ------------------------------------ */
+                /* a Jacobian rebuild requested by the previous sample runs first, one
+                 * transform per iteration (see trace_kernel) */
+                if (LLA && !started && (SI(I_PEND) != 0) && (mode != MODE_REBUILD)) {
+                        SI(I_RESUME) = mode;
+                        SI(I_RB_AXIS) = 0;
+                        mode = MODE_REBUILD;
+                }
+                if (mode == MODE_FINISH) { /* a finished particle whose rebuild is done */
+                        finish = true;
+                        step_out = SF(F_DS0);
+                } else if (!started) {
+                        /* ---- one ECEF -> geodetic transform ------------------------- */
                         tb::Sample S;
                         {
-                                double step = 0.;
-                                if (mode == MODE_TENT)
-                                        step = SF(F_DS);
-                                else if (mode == MODE_BISECT)
-                                        step = 0.5 * (SF(F_DS0) + SF(F_DS1));
-                                double p[3] = { SF(F_POS), SF(F_POS + 1), SF(F_POS + 2) };
-                                if (mode != MODE_INIT) {
-                                        p[0] += SF(F_DIR) * step;
-                                        p[1] += SF(F_DIR + 1) * step;
-                                        p[2] += SF(F_DIR + 2) * step;
+                                double p[3];
+                                int rb_t = 0, rb_axis = 0;
+                                bool heavy = true;
+                                if (LLA && (mode == MODE_REBUILD)) {
+                                        rb_t = __ffs(SI(I_PEND)) - 1;
+                                        rb_axis = SI(I_RB_AXIS);
+                                        p[0] = lla[rb_t].ref_ecef[0];
+                                        p[1] = lla[rb_t].ref_ecef[1];
+                                        p[2] = lla[rb_t].ref_ecef[2];
+                                        if (rb_axis == 0) p[0] += 10.;
+                                        else if (rb_axis == 1) p[1] += 10.;
+                                        else p[2] += 10.;
+                                } else {
+                                        double step = 0.;
+                                        if (mode == MODE_TENT)
+                                                step = SF(F_DS);
+                                        else if (mode == MODE_BISECT)
+                                                step = 0.5 * (SF(F_DS0) + SF(F_DS1));
+                                        p[0] = SF(F_POS);
+                                        p[1] = SF(F_POS + 1);
+                                        p[2] = SF(F_POS + 2);
+                                        if (mode != MODE_INIT) {
+                                                p[0] += SF(F_DIR) * step;
+                                                p[1] += SF(F_DIR + 1) * step;
+                                                p[2] += SF(F_DIR + 2) * step;
+                                        }
+                                        heavy = tb::needs_geodetic<LLA>(G, lla, p);
+                                }
+                                double pre[3] = { 0., 0., 0. };
+                                if (heavy) tb::geodetic_with_geoid(G, p, pre);
+                                if (LLA && (mode == MODE_REBUILD)) {
+                                        tb::rebuild_column<PROJ>(G, lla[rb_t], G.transforms[rb_t],
+                                            ((SI(I_PEND_N0) >> rb_t) & 1) ? 3 : 0, rb_axis, pre);
+                                        if (rb_axis == 2) {
+                                                SI(I_PEND) &= ~(1 << rb_t);
+                                                SI(I_RB_AXIS) = 0;
+                                                if (SI(I_PEND) == 0) mode = SI(I_RESUME);
+                                        } else {
+                                                SI(I_RB_AXIS) = rb_axis + 1;
+                                        }
+                                        continue;
                                 }
                                 double last_pos[3] = { SF(F_LASTPOS), SF(F_LASTPOS + 1),
                                         SF(F_LASTPOS + 2) };
-                                tb::sample_geometry<LLA, PROJ>(
-                                    G, lla, last_pos, mode != MODE_BISECT, p, S);
+                                tb::Pending pending = { 0u, 0u };
+                                tb::sample_geometry<LLA, PROJ, true>(G, lla, last_pos,
+                                    mode != MODE_BISECT, p, S, heavy ? pre : NULL, &pending);
+                                if (LLA) {
+                                        SI(I_PEND) = (int)pending.mask;
+                                        SI(I_PEND_N0) = (int)pending.n0;
+                                }
                                 if (mode != MODE_BISECT) {
                                         SF(F_LASTPOS) = last_pos[0];
                                         SF(F_LASTPOS + 1) = last_pos[1];
@@ -585,6 +691,13 @@ __global__ void __launch_bounds__(128, 5)
                         }
                 }
                 if (!finish) continue;
+                if (LLA && (SI(I_PEND) != 0)) {
+                        /* the state to save must include the pending Jacobian: finish
+                         * once the rebuild iterations are through */
+                        SF(F_DS0) = step_out;
+                        mode = MODE_FINISH;
+                        continue;
+                }
 
                 /* ---- outputs and state of a finished particle ---------------------- */
                 const unsigned long long r = ((unsigned long long)(unsigned)SI(I_RAYHI) << 32) |
@@ -608,19 +721,16 @@ __global__ void __launch_bounds__(128, 5)
                         A.index[2 * r + 1] = SI(I_IDX1);
                 }
                 if (A.states != NULL) {
-                        ParticleState * ps = A.states + r;
-                        ps->st.last_position[0] = SF(F_LASTPOS);
-                        ps->st.last_position[1] = SF(F_LASTPOS + 1);
-                        ps->st.last_position[2] = SF(F_LASTPOS + 2);
-                        ps->st.last.lat = SF(F_LAT);
-                        ps->st.last.lon = SF(F_LON);
-                        ps->st.last.alt = SF(F_ALT);
-                        ps->st.last.elev0 = SF(F_ELEV0);
-                        ps->st.last.elev1 = SF(F_ELEV1);
-                        ps->st.last.idx0 = idx0;
-                        ps->st.last.idx1 = SI(I_IDX1);
-                        if (LLA)
-                                for (int t = 0; t < G.n_transforms; t++) ps->lla[t] = lla[t];
+                        double * ps = A.states + r;
+                        ps[(PS_LASTPOS + 0) * A.stride] = SF(F_LASTPOS);
+                        ps[(PS_LASTPOS + 1) * A.stride] = SF(F_LASTPOS + 1);
+                        ps[(PS_LASTPOS + 2) * A.stride] = SF(F_LASTPOS + 2);
+                        ps[PS_LAT * A.stride] = SF(F_LAT);
+                        ps[PS_LON * A.stride] = SF(F_LON);
+                        ps[PS_ALT * A.stride] = SF(F_ALT);
+                        ps[PS_ELEV0 * A.stride] = SF(F_ELEV0);
+                        ps[PS_ELEV1 * A.stride] = SF(F_ELEV1);
+                        ps[PS_INDEX * A.stride] = __hiloint2double(SI(I_IDX1), idx0);
                 }
                 mode = MODE_IDLE;
         }
@@ -637,15 +747,19 @@ __global__ void __launch_bounds__(128, 5)
         }
 }
 
-__global__ void states_reset_kernel(ParticleState * states, unsigned long long n)
+/* turtle_stepper_reset for every particle (stepper.c:602-615): last position and every
+ * reference point at DBL_MAX; the last sample is cleared. */
+__global__ void states_reset_kernel(double * states, tb::LlaState * lla_states,
+    unsigned long long stride, unsigned long long n, int n_transforms)
 {
-        const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+        const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
         for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-             i < n; i += stride) {
-                tb::state_reset(states[i].st, states[i].lla, tb::MAX_TRANSFORMS);
-                states[i].st.last.idx0 = states[i].st.last.idx1 = -1;
-                states[i].st.last.lat = states[i].st.last.lon = states[i].st.last.alt = 0.;
-                states[i].st.last.elev0 = states[i].st.last.elev1 = 0.;
+             i < n; i += step) {
+                double * ps = states + i;
+                for (int k = 0; k < 3; k++) ps[(PS_LASTPOS + k) * stride] = DBL_MAX;
+                for (int k = PS_LAT; k < PS_INDEX; k++) ps[k * stride] = 0.;
+                ps[PS_INDEX * stride] = __hiloint2double(-1, -1);
+                tb::lla_reset(lla_states + i * (unsigned long long)n_transforms, n_transforms);
         }
 }
 
@@ -901,7 +1015,10 @@ struct turtle_plan {
 struct turtle_states {
         struct turtle_plan * plan;
         size_t n;
-        ParticleState * d_states;
+        double * d_states;
+        tb::LlaState * d_lla;
+        size_t stride; /* particles per field row */
+        int n_transforms;
 };
 
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -1371,8 +1488,15 @@ extern "C" enum turtle_return turtle_states_create(
         states->plan = plan;
         states->n = n;
         states->d_states = NULL;
+        states->stride = (std::max<size_t>(n, 1) + 31) / 32 * 32;
+        states->n_transforms = plan->G.n_transforms;
+        states->d_lla = NULL;
         cudaError_t err = cudaMalloc((void **)&states->d_states,
-            std::max<size_t>(n, 1) * sizeof(ParticleState));
+            states->stride * PS_FIELDS * sizeof(double));
+        if (err == cudaSuccess)
+                err = cudaMalloc((void **)&states->d_lla, std::max<size_t>(n, 1) *
+                        std::max(states->n_transforms, 1) * sizeof(tb::LlaState));
+        if (err != cudaSuccess) cudaFree(states->d_states);
         if (err != cudaSuccess) {
                 delete states;
                 return tbh::raise(FN(&turtle_states_create), TURTLE_RETURN_MEMORY_ERROR,
@@ -1388,6 +1512,7 @@ extern "C" void turtle_states_destroy(struct turtle_states ** states)
         if ((states == NULL) || (*states == NULL)) return;
         cudaSetDevice((*states)->plan->device);
         cudaFree((*states)->d_states);
+        cudaFree((*states)->d_lla);
         delete *states;
         *states = NULL;
 }
@@ -1398,7 +1523,8 @@ extern "C" enum turtle_return turtle_states_reset(struct turtle_states * states)
         if (states->n == 0) return TURTLE_RETURN_SUCCESS;
         const int blocks = (int)std::min<size_t>((states->n + 255) / 256,
             (size_t)states->plan->sm_count * 8);
-        states_reset_kernel<<<blocks, 256>>>(states->d_states, states->n);
+        states_reset_kernel<<<blocks, 256>>>(states->d_states, states->d_lla, states->stride,
+            states->n, states->n_transforms);
         states->plan->counters.launches++;
         CUDA_TRY(&turtle_states_reset, cudaGetLastError());
         CUDA_TRY(&turtle_states_reset, cudaDeviceSynchronize());
@@ -1420,6 +1546,8 @@ extern "C" enum turtle_return turtle_stepper_step_batch_device(
         StepArgs A;
         A.n = n;
         A.states = (states != NULL) ? states->d_states : NULL;
+        A.lla_states = (states != NULL) ? states->d_lla : NULL;
+        A.stride = (states != NULL) ? states->stride : 0;
         A.position = position;
         A.direction = direction;
         A.latitude = latitude;
