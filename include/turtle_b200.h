@@ -195,6 +195,21 @@ TURTLE_API enum turtle_return turtle_map_elevation_ecef_batch_device(
     double * longitude, double * altitude, double * z, int * inside,
     void * stream);
 
+/* ---- projections (ref: turtle_projection_project / _unproject, src/turtle/projection.c:
+ * 192-233). Run on the current CUDA device. */
+TURTLE_API enum turtle_return turtle_projection_project_batch(
+    const struct turtle_projection * projection, size_t n, const double * latitude,
+    const double * longitude, double * x, double * y);
+TURTLE_API enum turtle_return turtle_projection_project_batch_device(
+    const struct turtle_projection * projection, size_t n, const double * latitude,
+    const double * longitude, double * x, double * y, void * stream);
+TURTLE_API enum turtle_return turtle_projection_unproject_batch(
+    const struct turtle_projection * projection, size_t n, const double * x,
+    const double * y, double * latitude, double * longitude);
+TURTLE_API enum turtle_return turtle_projection_unproject_batch_device(
+    const struct turtle_projection * projection, size_t n, const double * x,
+    const double * y, double * latitude, double * longitude, void * stream);
+
 /* ---- gradients (ref: turtle_map_gradient, src/turtle/map.c:280-378)
  * Same bits as the scalar call, including its first-row behaviour (map.c:353).
  * gx[i], gy[i] are untouched where inside[i] == 0. */

@@ -148,6 +148,26 @@ def test_geoid_style_geodetic_map(ora):
     assert np.array_equal(win, gin) and np.array_equal(wz[win == 1], gz[gin == 1])
 
 
+@pytest.mark.parametrize("tag", ["UTM 31N", "UTM 3.0S", "Lambert 93", "Lambert IIe"])
+def test_projection_batches(ora, tag):
+    """batched project / unproject vs the oracle. Everything here goes
+    through transcendentals (CUDA libm vs glibc): x, y within 2e-8 m (a few ulp of 1e7),
+    latitude / longitude within 1e-12 deg plus, for Lambert, the FLT_EPSILON stopping rule
+    of the reference's inverse iteration (projection.c:265)."""
+    rng = np.random.default_rng(17)
+    n = 1 << 17
+    la, lo = rng.uniform(41., 51., n), rng.uniform(-5., 9., n)
+    p = tb.Projection(tag)
+    wx, wy = ora.project(tag, la, lo)
+    gx, gy = p.project_batch(la, lo)
+    assert np.abs(wx - gx).max() < 2e-8 and np.abs(wy - gy).max() < 2e-8
+    wla, wlo = ora.project(tag, wx, wy, inverse=True)
+    gla, glo = p.unproject_batch(wx, wy)
+    tol = 1e-12 if tag.startswith("UTM") else 2e-8
+    assert np.abs(wla - gla).max() < tol and np.abs(wlo - glo).max() < 1e-12
+    assert np.abs(gla - la).max() < 5e-8 and np.abs(glo - lo).max() < 1e-8  # round trip
+
+
 def test_empty_batches():
     la, lo, al = tb.ecef_to_geodetic_batch(np.zeros((0, 3)))
     assert len(la) == 0

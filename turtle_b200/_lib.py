@@ -132,6 +132,10 @@ SIGNATURES = {
     "turtle_map_elevation_batch_device": (_I, [_P, _N, _P, _P, _P, _P, _P]),
     "turtle_map_elevation_ecef_batch": (_I, [_P, _N, _P, _P, _P, _P, _P, _P]),
     "turtle_map_elevation_ecef_batch_device": (_I, [_P, _N, _P, _P, _P, _P, _P, _P, _P]),
+    "turtle_projection_project_batch": (_I, [_P, _N, _P, _P, _P, _P]),
+    "turtle_projection_project_batch_device": (_I, [_P, _N, _P, _P, _P, _P, _P]),
+    "turtle_projection_unproject_batch": (_I, [_P, _N, _P, _P, _P, _P]),
+    "turtle_projection_unproject_batch_device": (_I, [_P, _N, _P, _P, _P, _P, _P]),
     "turtle_map_gradient_batch": (_I, [_P, _N, _P, _P, _P, _P, _P]),
     "turtle_map_gradient_batch_device": (_I, [_P, _N, _P, _P, _P, _P, _P, _P]),
     "turtle_map_fill_batch": (_I, [_P, _P]),

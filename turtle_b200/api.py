@@ -138,6 +138,20 @@ class Projection:
         _check(lib.turtle_projection_unproject(self._p, x, y, C.byref(la), C.byref(lo)))
         return la.value, lo.value
 
+    def project_batch(self, latitude, longitude):
+        la, lo = _f8(latitude), _f8(longitude)
+        x, y = np.empty(len(la)), np.empty(len(la))
+        _check(lib.turtle_projection_project_batch(self._p, len(la), _ptr(la), _ptr(lo),
+                                                   _ptr(x), _ptr(y)))
+        return x, y
+
+    def unproject_batch(self, x, y):
+        x, y = _f8(x), _f8(y)
+        la, lo = np.empty(len(x)), np.empty(len(x))
+        _check(lib.turtle_projection_unproject_batch(self._p, len(x), _ptr(x), _ptr(y),
+                                                     _ptr(la), _ptr(lo)))
+        return la, lo
+
     def __del__(self):
         if getattr(self, "_p", None):
             lib.turtle_projection_destroy(C.byref(self._p))

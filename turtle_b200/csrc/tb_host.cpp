@@ -194,61 +194,12 @@ void tbh::projection_to_desc(const struct turtle_projection * p, tb::ProjDesc * 
                 d->alpha[1] = n * n * (13. / 48. - 3. / 5. * n);
                 d->alpha[2] = 61. / 240. * n * n * n;
                 d->c = 2. * sqrt(n) / (1. + n);
-        }
-}
-
-/* ref: utm_xy_to_ll, projection.c:417-448 */
-static void utm_unproject(const struct turtle_projection * p, double x, double y,
-    double * latitude, double * longitude)
-{
-        const double a = UTM_A, f = UTM_F, k0 = UTM_K0;
-        const double E0 = 5E+05;
-        const double N0 = (p->utm_hemisphere > 0) ? 0. : 1E+07;
-        const double n = f / (2. - f);
-        const double A = a / (1. + n) * (1. + n * n * (0.25 + 0.0625 * n * n));
-        const double beta[3] = { n * (0.5 + n * (-2. / 3. + 37. / 96. * n)),
-                n * n * (1. / 48. + 1. / 15. * n), 17. / 480. * n * n * n };
-        const double delta[3] = { n * (2. + n * (-2. / 3. - 2. * n)),
-                n * n * (7. / 3. - 8. / 5. * n), 56. / 15. * n * n * n };
-        const double zeta0 = (y - N0) / (k0 * A);
-        const double eta0 = (x - E0) / (k0 * A);
-        double zeta = zeta0, eta = eta0;
-        for (int i = 0; i < 3; i++) {
-                const double k = 2. * (i + 1);
-                zeta -= beta[i] * sin(k * zeta0) * cosh(k * eta0);
-                eta -= beta[i] * cos(k * zeta0) * sinh(k * eta0);
-        }
-        const double chi = asin(sin(zeta) / cosh(eta));
-        double s = 0.;
-        for (int i = 0; i < 3; i++) s += delta[i] * sin(2. * (i + 1) * chi);
-        *latitude = (chi + s) * 180. / M_PI;
-        *longitude = p->utm_longitude_0 + atan2(sinh(eta), cos(zeta)) * 180. / M_PI;
-}
-
-/* ref: lambert_iso_to_latitude + lambert_xy_to_ll, projection.c:254-268,304-316 */
-static void lambert_unproject(const struct turtle_projection * p, double x, double y,
-    double * latitude, double * longitude)
-{
-        const double * q = LAMBERT[p->lambert_tag];
-        const double e = q[0], n = q[1], c = q[2], lambda_c = q[3];
-        const double dx = x - q[4];
-        const double dy = y - q[5];
-        const double R = sqrt(dx * dx + dy * dy);
-        const double gamma = atan2(dx, -dy);
-        *longitude = (lambda_c + gamma / n) * 180. / M_PI;
-        const double L = -log(R / c) / n;
-        const double eL = exp(L);
-        double phi0 = 2. * atan(eL) - 0.5 * M_PI;
-        for (;;) {
-                const double s = sin(phi0);
-                const double phi1 =
-                    2. * atan(pow((1. + e * s) / (1. - e * s), 0.5 * e) * eL) -
-                    0.5 * M_PI;
-                if (fabs(phi1 - phi0) <= (double)FLT_EPSILON) {
-                        *latitude = phi1 / M_PI * 180.;
-                        return;
-                }
-                phi0 = phi1;
+                d->beta[0] = n * (0.5 + n * (-2. / 3. + 37. / 96. * n));
+                d->beta[1] = n * n * (1. / 48. + 1. / 15. * n);
+                d->beta[2] = 17. / 480. * n * n * n;
+                d->delta[0] = n * (2. + n * (-2. / 3. - 2. * n));
+                d->delta[1] = n * n * (7. / 3. - 8. / 5. * n);
+                d->delta[2] = 56. / 15. * n * n * n;
         }
 }
 
@@ -323,10 +274,9 @@ extern "C" enum turtle_return turtle_projection_unproject(
         if (projection->type < 0)
                 return RAISE(&turtle_projection_unproject,
                     TURTLE_RETURN_BAD_PROJECTION, PROJ_C, "invalid projection");
-        if (projection->type == 0)
-                lambert_unproject(projection, x, y, latitude, longitude);
-        else
-                utm_unproject(projection, x, y, latitude, longitude);
+        tb::ProjDesc d;
+        tbh::projection_to_desc(projection, &d);
+        tb::unproject(d, x, y, *latitude, *longitude);
         return TURTLE_RETURN_SUCCESS;
 }
 

@@ -859,6 +859,25 @@ __global__ void __launch_bounds__(256) from_horizontal_kernel(unsigned long long
         }
 }
 
+/* ---- projections (ref: projection.c:192-233) ------------------- */
+
+__global__ void __launch_bounds__(256) projection_kernel(const tb::ProjDesc P, int inverse,
+    unsigned long long n, const double * __restrict__ a, const double * __restrict__ b,
+    double * __restrict__ c, double * __restrict__ d)
+{
+        const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+             i < n; i += stride) {
+                double u, v;
+                if (inverse)
+                        tb::unproject(P, a[i], b[i], u, v);
+                else
+                        tb::project(P, a[i], b[i], u, v);
+                c[i] = u;
+                d[i] = v;
+        }
+}
+
 /* ---- elevation kernels (ref: map.c:229-277) -------------------------------- */
 
 __global__ void __launch_bounds__(256) map_elevation_kernel(const tb::MapDesc M,
@@ -1795,6 +1814,74 @@ extern "C" enum turtle_return turtle_ecef_from_horizontal_batch(size_t n,
         return TURTLE_RETURN_SUCCESS;
 }
 
+/* ---- projections ------------------------------------------------------------------- */
+
+static enum turtle_return projection_batch(turtle_function_t * fn,
+    const struct turtle_projection * projection, int inverse, size_t n, const double * a,
+    const double * b, double * c, double * d, bool on_device, void * stream)
+{
+        if (projection == NULL)
+                return tbh::raise(fn, TURTLE_RETURN_BAD_ADDRESS, "src/turtle/projection.c",
+                    __LINE__, "missing projection");
+        if (projection->type < 0)
+                return tbh::raise(fn, TURTLE_RETURN_BAD_PROJECTION, "src/turtle/projection.c",
+                    __LINE__, "invalid projection");
+        enum turtle_return rc = require_current(fn);
+        if ((rc != TURTLE_RETURN_SUCCESS) || (n == 0)) return rc;
+        tb::ProjDesc P;
+        tbh::projection_to_desc(projection, &P);
+        if (on_device) {
+                projection_kernel<<<stream_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(
+                    P, inverse, n, a, b, c, d);
+                CUDA_TRY(fn, cudaGetLastError());
+                return TURTLE_RETURN_SUCCESS;
+        }
+        DeviceBuffers B;
+        double *d_a, *d_b, *d_c, *d_d;
+        DEV_IN(fn, B, d_a, a, n * sizeof(double));
+        DEV_IN(fn, B, d_b, b, n * sizeof(double));
+        DEV_OUT(fn, B, d_c, c, n * sizeof(double));
+        DEV_OUT(fn, B, d_d, d, n * sizeof(double));
+        projection_kernel<<<stream_blocks(n, 256), 256>>>(P, inverse, n, d_a, d_b, d_c, d_d);
+        CUDA_TRY(fn, cudaGetLastError());
+        CUDA_TRY(fn, cudaDeviceSynchronize());
+        DEV_BACK(fn, c, d_c, n * sizeof(double));
+        DEV_BACK(fn, d, d_d, n * sizeof(double));
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_projection_project_batch(
+    const struct turtle_projection * projection, size_t n, const double * latitude,
+    const double * longitude, double * x, double * y)
+{
+        return projection_batch(FN(&turtle_projection_project_batch), projection, 0, n, latitude,
+            longitude, x, y, false, NULL);
+}
+
+extern "C" enum turtle_return turtle_projection_project_batch_device(
+    const struct turtle_projection * projection, size_t n, const double * latitude,
+    const double * longitude, double * x, double * y, void * stream)
+{
+        return projection_batch(FN(&turtle_projection_project_batch_device), projection, 0, n,
+            latitude, longitude, x, y, true, stream);
+}
+
+extern "C" enum turtle_return turtle_projection_unproject_batch(
+    const struct turtle_projection * projection, size_t n, const double * x, const double * y,
+    double * latitude, double * longitude)
+{
+        return projection_batch(FN(&turtle_projection_unproject_batch), projection, 1, n, x, y,
+            latitude, longitude, false, NULL);
+}
+
+extern "C" enum turtle_return turtle_projection_unproject_batch_device(
+    const struct turtle_projection * projection, size_t n, const double * x, const double * y,
+    double * latitude, double * longitude, void * stream)
+{
+        return projection_batch(FN(&turtle_projection_unproject_batch_device), projection, 1, n,
+            x, y, latitude, longitude, true, stream);
+}
+
 /* ---- map mirrors and elevation queries -------------------------------------------- */
 
 static std::mutex g_mirror_mutex;
@@ -2021,6 +2108,10 @@ extern "C" const char * tb_batch_function_name(turtle_function_t * caller)
         NAME(turtle_map_elevation_batch_device);
         NAME(turtle_map_elevation_ecef_batch);
         NAME(turtle_map_elevation_ecef_batch_device);
+        NAME(turtle_projection_project_batch);
+        NAME(turtle_projection_project_batch_device);
+        NAME(turtle_projection_unproject_batch);
+        NAME(turtle_projection_unproject_batch_device);
         NAME(turtle_map_gradient_batch);
         NAME(turtle_map_gradient_batch_device);
 #undef NAME
