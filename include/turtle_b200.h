@@ -118,6 +118,11 @@ TURTLE_API void turtle_plan_launch_set(
  * direction (grazing rays take the most steps; a long ray that starts last bounds the
  * kernel time). Results do not depend on the mode, only the time does. */
 TURTLE_API void turtle_plan_schedule_set(struct turtle_plan * plan, int mode);
+/* Kernel specialisation by geometry shape. 1 (default): a geometry made of one layer with
+ * one uniform geodetic stack (no geoid, range 0) runs a kernel with the list walk of
+ * stepper_sample (stepper.c:717-743) resolved at compile time. 0: always the generic
+ * kernel. Results are byte-identical (tests/test_gpu_trace.py); only the time differs. */
+TURTLE_API void turtle_plan_specialise_set(struct turtle_plan * plan, int enable);
 
 /* ---- whole rays: reset, query, then step until the rule stops the ray ------ */
 TURTLE_API enum turtle_return turtle_stepper_trace_batch(

@@ -156,6 +156,10 @@ def test_determinism_and_chunking(small_stack):
     c = plan.trace(pos, dirs, rule)
     assert a.tobytes() == c.tobytes()
     plan.schedule_set(0)
+    plan.specialise_set(0)  # generic list-walking kernel instead of the single-stack one
+    c = plan.trace(pos, dirs, rule)
+    assert a.tobytes() == c.tobytes()
+    plan.specialise_set(1)
     d_res = torch.empty((n, 96), dtype=torch.uint8, device="cuda:0")
     plan.trace_device(n, torch.from_numpy(pos).cuda(), torch.from_numpy(dirs).cuda(), rule, d_res)
     torch.cuda.synchronize()

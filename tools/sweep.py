@@ -29,10 +29,13 @@ def main():
     d_pos, d_dir = h_pos.cuda(), h_dir.cuda()
     d_res = torch.empty((n, 96), dtype=torch.uint8, device="cuda")
     res_np = h_res.numpy().view(tb.TRACE_RESULT).reshape(n)
-    configs = [(5, 128, 0), (6, 128, 0), (8, 128, 0)]
-    for (c, t, sched) in configs:
+    configs = [(6, 128, 0, 0), (6, 128, 0, 1), (8, 128, 0, 1)]
+    if os.environ.get("SWEEP_CONFIGS"):
+        configs = [tuple(int(v) for v in c.split(",")) for c in os.environ["SWEEP_CONFIGS"].split(";")]
+    for (c, t, sched, special) in configs:
         plan.launch_set(c, t)
         plan.schedule_set(sched)
+        plan.specialise_set(special)
         for _ in range(2):
             plan.trace_device(n, d_pos, d_dir, rule, d_res)
         torch.cuda.synchronize()
@@ -48,7 +51,7 @@ def main():
             plan.trace(h_pos.numpy(), h_dir.numpy(), rule, results=res_np)
         host_ms = (time.perf_counter() - t0) / 2 * 1e3
         c2 = plan.counters()
-        print(json.dumps(dict(order=order, schedule=sched, ctas_per_sm=c, threads=t, device_ms=round(ms, 2), mrays=round(n / ms / 1e3, 2),
+        print(json.dumps(dict(order=order, schedule=sched, special=special, ctas_per_sm=c, threads=t, device_ms=round(ms, 2), mrays=round(n / ms / 1e3, 2),
                               host_ms=round(host_ms, 2), host_mrays=round(n / host_ms / 1e3, 2),
                               host_kernel_ms_sum=round(c2["kernel_ms"], 1))), flush=True)
 

@@ -110,6 +110,7 @@ SIGNATURES = {
     "turtle_plan_counters_sync": (None, [_P]),
     "turtle_plan_launch_set": (None, [_P, _I, _I]),
     "turtle_plan_schedule_set": (None, [_P, _I]),
+    "turtle_plan_specialise_set": (None, [_P, _I]),
     # rays
     "turtle_stepper_trace_batch": (_I, [_P, _N, _P, _P, C.POINTER(TraceRule), _P]),
     "turtle_stepper_trace_batch_device": (_I, [_P, _N, _P, _P, C.POINTER(TraceRule), _P, _P]),

@@ -349,6 +349,9 @@ class Plan:
     def schedule_set(self, mode):
         lib.turtle_plan_schedule_set(self._p, mode)
 
+    def specialise_set(self, enable):
+        lib.turtle_plan_specialise_set(self._p, int(enable))
+
     def counters(self, sync=False):
         if sync:
             lib.turtle_plan_counters_sync(self._p)

@@ -300,8 +300,7 @@ static tb::MapDesc map_desc(const struct turtle_map * map)
         d.dy = map->dy;
         d.z0 = map->z0;
         d.dz = map->dz;
-        d.nx1 = (double)(map->nx - 1);
-        d.ny1 = (double)(map->ny - 1);
+        tb::map_desc_finish(d);
         return d;
 }
 
@@ -876,10 +875,10 @@ static enum turtle_return stack_elevation_scalar(struct turtle_stack * stack,
                                 hgt_parse_name(stack->path[cell].c_str(), &nxy, &x0, &y0);
                                 tb::MapDesc d;
                                 d.nx = d.ny = nxy;
-                                d.nx1 = d.ny1 = (double)(nxy - 1);
                                 d.x0 = x0;
                                 d.y0 = y0;
                                 d.dx = d.dy = 1. / (nxy - 1);
+                                tb::map_desc_finish(d);
                                 if (!tb::tile_owns(d, latitude, longitude)) continue;
                                 enum turtle_return rc = stack_load_cell(stack, cell, caller);
                                 if (rc != TURTLE_RETURN_SUCCESS) {
@@ -1346,6 +1345,8 @@ enum turtle_return tbh::stepper_flatten(struct turtle_stepper * s,
                                 S.dz = first->dz;
                                 S.nx1 = (double)(first->nx - 1);
                                 S.ny1 = (double)(first->ny - 1);
+                                S.rdx = 1. / S.dx;
+                                S.rdy = 1. / S.dy;
                         } else {
                                 S.uniform = 0;
                         }
@@ -1355,6 +1356,20 @@ enum turtle_return tbh::stepper_flatten(struct turtle_stepper * s,
                         }
                         S.nlat_d = (double)S.nlat;
                         S.nlon_d = (double)S.nlon;
+                        /* do all tiles cover exactly their grid cell? (tb::stack_elevation) */
+                        S.aligned = (S.dlat > 0.) && (S.dlon > 0.) && !st->tile.empty();
+                        for (size_t c = 0; S.aligned && (c < st->tile.size()); c++) {
+                                const struct turtle_map * t = st->tile[c];
+                                if (t == NULL) continue;
+                                const double ix = (double)(c % (size_t)S.nlon);
+                                const double iy = (double)(c / (size_t)S.nlon);
+                                const double tol = 1E-09;
+                                if (!(fabs((t->x0 - S.lon0) / S.dlon - ix) <= tol) ||
+                                    !(fabs((t->y0 - S.lat0) / S.dlat - iy) <= tol) ||
+                                    !(fabs((t->nx - 1) * t->dx / S.dlon - 1.) <= tol) ||
+                                    !(fabs((t->ny - 1) * t->dy / S.dlat - 1.) <= tol))
+                                        S.aligned = 0;
+                        }
                 }
         }
         G.geoid = -1;

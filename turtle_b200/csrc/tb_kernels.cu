@@ -90,7 +90,7 @@ __device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory")
 
 /* The persistent ray-tracing kernel. MINB = CTAs of 128 threads per SM the register
  * allocation is bounded for (occupancy vs registers is a measured trade). */
-template <bool LLA, bool PROJ, int MINB>
+template <bool LLA, bool PROJ, int MINB, int SHAPE = tb::SHAPE_GENERIC>
 __global__ void __launch_bounds__(128, MINB)
     trace_kernel(const __grid_constant__ tb::Geometry G, const TraceArgs A)
 {
@@ -189,7 +189,18 @@ __global__ void __launch_bounds__(128, MINB)
                         mode = MODE_REBUILD;
                 }
                 tb::Sample S;
-                {
+                if (SHAPE == tb::SHAPE_STACK) {
+                        /* one layer, one uniform geodetic stack: no list walk */
+                        double p[3] = { SF(F_POS), SF(F_POS + 1), SF(F_POS + 2) };
+                        if (mode != MODE_INIT) {
+                                const double step = (mode == MODE_TENT) ?
+                                    SF(F_DS) : 0.5 * (SF(F_DS0) + SF(F_DS1));
+                                p[0] += SF(F_DIR) * step;
+                                p[1] += SF(F_DIR + 1) * step;
+                                p[2] += SF(F_DIR + 2) * step;
+                        }
+                        tb::sample_single_stack(G, p, S);
+                } else {
                         double p[3];
                         int rb_t = 0, rb_axis = 0;
                         bool heavy = true;
@@ -976,6 +987,20 @@ __global__ void divide_selftest_kernel(unsigned long long n, unsigned long long 
                 if (tb::divide(0., d) != 0. || tb::divide(b, d) != 1.) bad++;
                 const int k = (int)(mix64(i) & 0xffff) - 32768;
                 if (tb::int_to_double(k) != (double)k) bad++;
+                /* tb::sqrt_in_range against the library's sqrt over its whole range */
+                const double sq = fabs(random_double(seed + 2ull * i + 7ull, -960, 1020));
+                if (__double_as_longlong(tb::sqrt_in_range(sq)) != __double_as_longlong(sqrt(sq)))
+                        bad++;
+                const double sq1 = 0.25 + 0.75 * fabs(random_double(seed + 2ull * i + 9ull, -1, -1));
+                if (__double_as_longlong(tb::sqrt_in_range(sq1)) != __double_as_longlong(sqrt(sq1)))
+                        bad++;
+                /* divisors with a correctly rounded reciprocal (tb::known_divisor): the
+                 * random one, pi (degrees) and the usual grid pitches */
+                const double fixed[6] = { b, M_PI, 1. / 3600., 1. / 1200., 10., 1. / 3. };
+                const double c = fixed[i % 6ull];
+                const tb::Divisor kd = tb::known_divisor(c, 1. / c);
+                if (__double_as_longlong(tb::divide(a, kd)) != __double_as_longlong(a / c)) bad++;
+                if (__double_as_longlong(tb::divide(a2, kd)) != __double_as_longlong(a2 / c)) bad++;
         }
         if (bad) atomicAdd(mismatches, bad);
 }
@@ -1020,6 +1045,7 @@ struct turtle_plan {
         turtle_plan_counters counters;
         /* ray scheduling (turtle_plan_schedule_set) */
         int schedule;
+        int specialise; /* turtle_plan_specialise_set */
         unsigned * d_sched[4]; /* per pipeline slot: keys, index, keys', order */
         void * d_sched_tmp[4];
         size_t sched_rays[4], sched_tmp_bytes[4];
@@ -1127,6 +1153,7 @@ extern "C" enum turtle_return turtle_stepper_freeze(
         plan->d_tiles = NULL;
         plan->d_counters = NULL;
         plan->schedule = 0;
+        plan->specialise = 1;
         for (int s = 0; s < 4; s++) {
                 plan->d_sched[s] = NULL;
                 plan->d_sched_tmp[s] = NULL;
@@ -1260,6 +1287,11 @@ extern "C" void turtle_plan_schedule_set(struct turtle_plan * plan, int mode)
         plan->schedule = mode;
 }
 
+extern "C" void turtle_plan_specialise_set(struct turtle_plan * plan, int enable)
+{
+        plan->specialise = enable;
+}
+
 /* Build the queue order of a launch (longest-expected-first) in plan->d_sched. */
 static cudaError_t schedule_rays(struct turtle_plan * plan, int slot, size_t n,
     const double * d_position, const double * d_direction, cudaStream_t stream,
@@ -1362,7 +1394,12 @@ static cudaError_t launch_trace(struct turtle_plan * plan, int slot, size_t n,
         } while (0)
         /* the register budget follows the requested residency (in units of 128 threads) */
         const int minb = per_sm * threads / 128;
-        if (minb <= 4)
+        if (plan->specialise && (tb::geometry_shape(plan->G) == tb::SHAPE_STACK)) {
+                if (minb <= 6)
+                        trace_kernel<false, false, 6, tb::SHAPE_STACK><<<blocks, threads, 0, stream>>>(plan->G, A);
+                else
+                        trace_kernel<false, false, 8, tb::SHAPE_STACK><<<blocks, threads, 0, stream>>>(plan->G, A);
+        } else if (minb <= 4)
                 TRACE_LAUNCH(4);
         else if (minb == 5)
                 TRACE_LAUNCH(5);
@@ -1938,8 +1975,7 @@ static enum turtle_return map_mirror(turtle_function_t * fn, struct turtle_map *
         desc->dy = map->dy;
         desc->z0 = map->z0;
         desc->dz = map->dz;
-        desc->nx1 = (double)(map->nx - 1);
-        desc->ny1 = (double)(map->ny - 1);
+        tb::map_desc_finish(*desc);
         return TURTLE_RETURN_SUCCESS;
 }
 
