@@ -255,13 +255,34 @@ def main():
     d_pos = h_pos.to(dev)
     d_dir = h_dir.to(dev)
     d_res = torch.empty((n, 96), dtype=torch.uint8, device=dev)
-    gathered = [torch.empty((n, 96), dtype=torch.uint8, device=dev) for _ in range(world)] \
-        if (world > 1 and rank == 0) else None
     stream = torch.cuda.current_stream()
 
+    # N > 1: the records of every rank land in rank 0's memory. The trace kernel of rank r
+    # stores them there itself, over NVLink, as its rays end (turtle_b200.dist.PeerRecords:
+    # rank 0's array mapped into every process by CUDA IPC): no gather after the kernel.
+    # Should the GPUs not reach each other, fall back to an NCCL gather of the records.
+    peer, gathered, exchange = None, None, "none (1 GPU)"
+    if world > 1:
+        from turtle_b200.dist import PeerRecords
+        ok = torch.ones(1, device=dev)
+        try:
+            peer = PeerRecords([n] * world, dst=0)
+        except Exception as err:  # noqa: BLE001 -- reported, then the gather path is used
+            sys.stderr.write("rank %d: peer mapping failed (%s)\n" % (rank, err))
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() > 0:
+            exchange = "peer stores from the trace kernel into rank 0's HBM (CUDA IPC over NVLink)"
+        else:
+            peer = None
+            exchange = "NCCL gather of the records on rank 0 after the kernel"
+            gathered = [torch.empty((n, 96), dtype=torch.uint8, device=dev)
+                        for _ in range(world)] if rank == 0 else None
+    out_ptr = peer.view if peer is not None else d_res
+
     def step_device():
-        plan.trace_device(n, d_pos, d_dir, rule, d_res, stream=stream.cuda_stream)
-        if world > 1:  # the only exchange of the path: gather the records on rank 0
+        plan.trace_device(n, d_pos, d_dir, rule, out_ptr, stream=stream.cuda_stream)
+        if world > 1 and peer is None:
             dist.gather(d_res, gathered, dst=0)
 
     def timed(fn, steps):
@@ -288,6 +309,11 @@ def main():
     for _ in range(args.warmup):
         step_device()
     torch.cuda.synchronize()
+    if peer is not None:  # mark every slot unwritten (status -1) before the timed steps
+        peer.ready()
+        if rank == 0:
+            peer.tensor.fill_(0xff)
+            torch.cuda.synchronize()
     sampler = ClockSampler(local) if rank == 0 else None
     ms_total, t0, t1 = timed(step_device, args.steps)
     clocks = sampler.stop(t0, t1) if sampler else None
@@ -295,6 +321,11 @@ def main():
     launches = args.steps
     ms_step = ms_total / args.steps
     value = world * n / (ms_step * 1e-3) / 1e6
+    if peer is not None and rank == 0:
+        # every rank's records are in rank 0's array: none of the slots is left unwritten
+        status = peer.tensor.view(world, n, 96)[:, :, 76:80].contiguous().view(torch.int32)
+        assert int((status < 0).sum().item()) == 0 and int((status > 4).sum().item()) == 0
+        d_res.copy_(peer.tensor[:n])
 
     # kernel alone (no gather), CUDA events on the launching stream: the roofline input
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -342,6 +373,9 @@ def main():
         same = bool((torch.from_numpy(h_res.numpy()) == d_res.cpu()).all())
         e2e["matches_device_path"] = same
 
+    if peer is not None:  # collective: the peers unmap before rank 0 frees
+        peer.close()
+        peer = None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -397,7 +431,7 @@ def main():
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(n, world),
+        "data": "synthetic", "config": dict(workload_config(n, world), exchange=exchange),
         "ns_per_step": kernel_ms * 1e6 / max(steps, 1),
         "steps_per_ray": steps / n, "samples_per_step": samples / max(steps, 1),
         "per_rank_kernel_ms": per_rank_kernel_ms,

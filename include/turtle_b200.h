@@ -246,6 +246,28 @@ TURTLE_API const char * turtle_b200_version(void);
  * differ in any bit (0 expected), -1 without a device. */
 TURTLE_API long long turtle_b200_selftest_division(size_t n, uint64_t seed);
 
+/* ---- multi-GPU: result records written straight into a peer GPU's memory ----------
+ * Rays shard across the GPUs of a box with the DEM replicated;
+ * the only exchange of the path is the delivery of the fixed-size result records to the
+ * rank that consumes them. Instead of a gather AFTER the kernel, the consumer allocates
+ * the whole result array once, exports it (CUDA IPC), and every other process opens it
+ * and passes `base + first_ray` as the `results` pointer of
+ * turtle_stepper_trace_batch_device: the trace kernel then stores each record over
+ * NVLink / NVSwitch the moment its ray ends, overlapped with the stepping of all other
+ * rays. One process per GPU; all GPUs of the box must be visible to every process. */
+#define TURTLE_B200_PEER_HANDLE_BYTES 64
+/* cudaMalloc on the current device (an allocation of its own: exportable). */
+TURTLE_API enum turtle_return turtle_b200_peer_alloc(size_t bytes, void ** device_pointer);
+TURTLE_API enum turtle_return turtle_b200_peer_free(void * device_pointer);
+/* Handle of an allocation made by turtle_b200_peer_alloc, to be sent to the peers. */
+TURTLE_API enum turtle_return turtle_b200_peer_export(
+    void * device_pointer, unsigned char handle[TURTLE_B200_PEER_HANDLE_BYTES]);
+/* Map a peer's allocation into this process (current device must be able to reach the
+ * owner over NVLink / PCIe peer access); close it before the owner frees it. */
+TURTLE_API enum turtle_return turtle_b200_peer_open(
+    const unsigned char handle[TURTLE_B200_PEER_HANDLE_BYTES], void ** device_pointer);
+TURTLE_API enum turtle_return turtle_b200_peer_close(void * device_pointer);
+
 #ifdef __cplusplus
 }
 #endif

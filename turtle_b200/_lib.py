@@ -111,6 +111,12 @@ SIGNATURES = {
     "turtle_plan_launch_set": (None, [_P, _I, _I]),
     "turtle_plan_schedule_set": (None, [_P, _I]),
     "turtle_plan_specialise_set": (None, [_P, _I]),
+    # peer memory
+    "turtle_b200_peer_alloc": (_I, [_N, _PP]),
+    "turtle_b200_peer_free": (_I, [_P]),
+    "turtle_b200_peer_export": (_I, [_P, _P]),
+    "turtle_b200_peer_open": (_I, [_P, _PP]),
+    "turtle_b200_peer_close": (_I, [_P]),
     # rays
     "turtle_stepper_trace_batch": (_I, [_P, _N, _P, _P, C.POINTER(TraceRule), _P]),
     "turtle_stepper_trace_batch_device": (_I, [_P, _N, _P, _P, C.POINTER(TraceRule), _P, _P]),

@@ -66,6 +66,8 @@ def _ptr(a):
         return None
     if isinstance(a, np.ndarray):
         return a.ctypes.data_as(C.c_void_p)
+    if isinstance(a, int):  # a raw device pointer (e.g. a peer mapping, dist.PeerRecords)
+        return C.c_void_p(a)
     return C.c_void_p(a.data_ptr())
 
 

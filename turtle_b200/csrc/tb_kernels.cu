@@ -76,15 +76,25 @@ __device__ __forceinline__ bool finite3(const double v[3])
  * one column per thread: conflict free). Nothing of it is needed while a sample is
  * being evaluated, so parking it here instead of in registers leaves the register
  * file to the FP64 code of the sample: no spills at 6 CTAs per SM. */
-enum { F_POS = 0, F_DIR = 3, F_LAT = 6, F_LON, F_ALT, F_ELEV0, F_ELEV1, F_DS, F_DS0, F_DS1,
-       F_LEN, F_TOTAL = F_LEN + TURTLE_TRACE_MEDIA, F_LASTPOS, N_F = F_LASTPOS + 3 };
+enum { F_POS = 0, F_DIR = 3, F_ALT = 6, F_ELEV0, F_ELEV1, F_DS, F_DS0, F_DS1,
+       F_LEN, F_TOTAL = F_LEN + TURTLE_TRACE_MEDIA,
+       N_F_BASE,                  /* rows of a trace without the local approximation */
+       F_LASTPOS = N_F_BASE,      /* + stepper->last.position (local approximation only) */
+       N_F_LLA = F_LASTPOS + 3,
+       F_LAT = N_F_LLA, F_LON,    /* + published latitude, longitude (step_batch only) */
+       N_F = F_LON + 1 };
 enum { I_IDX0 = 0, I_IDX1, I_MEDIUM0, I_NSTEPS, I_NCHANGES, I_HASH, I_RAYLO, I_RAYHI,
-       I_PEND, I_PEND_N0, I_RESUME, I_RB_AXIS, N_I };
+       N_I_BASE,
+       I_PEND = N_I_BASE, I_PEND_N0, I_RESUME, I_RB_AXIS, N_I };
 
-struct LaneStore {
-        double f[N_F][128];
-        int i[N_I][128];
+/* Only the rows a kernel uses are allocated: the shared memory a CTA does not take is
+ * L1 cache for the DEM gathers (17 + 4 kB per CTA for a trace without the local
+ * approximation: 6 CTAs per SM leave ~120 kB of L1 instead of 60 kB). */
+template <int NF, int NI> struct LaneStoreT {
+        double f[NF][128];
+        int i[NI][128];
 };
+typedef LaneStoreT<N_F, N_I> LaneStore;
 
 __device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
 
@@ -94,12 +104,14 @@ template <bool LLA, bool PROJ, int MINB, int SHAPE = tb::SHAPE_GENERIC>
 __global__ void __launch_bounds__(128, MINB)
     trace_kernel(const __grid_constant__ tb::Geometry G, const TraceArgs A)
 {
-        __shared__ LaneStore store;
+        constexpr int NF = LLA ? N_F_LLA : N_F_BASE, NI = LLA ? N_I : N_I_BASE;
+        __shared__ LaneStoreT<NF, NI> store;
         const unsigned tid = threadIdx.x;
         const unsigned lane = tid & 31u;
         const unsigned FULL = 0xffffffffu;
-#define SF(k) store.f[k][tid]
-#define SI(k) store.i[k][tid]
+        /* (rows beyond the allocation are only named in code that is compiled out) */
+#define SF(k) store.f[((k) < NF) ? (k) : 0][tid]
+#define SI(k) store.i[((k) < NI) ? (k) : 0][tid]
 
         int mode = MODE_IDLE;
         tb::LlaState lla[LLA ? tb::MAX_TRANSFORMS : 1];
@@ -140,7 +152,7 @@ __global__ void __launch_bounds__(128, MINB)
                                                 SI(I_NCHANGES) = 0;
                                                 SI(I_RAYLO) = (int)(unsigned)(r & 0xffffffffull);
                                                 SI(I_RAYHI) = (int)(unsigned)(r >> 32);
-                                                SI(I_PEND) = 0;
+                                                if (LLA) SI(I_PEND) = 0;
                                                 mode = MODE_INIT;
                                                 /* every ray starts from a reset stepper
                                                  * (turtle_stepper_reset, stepper.c:647-651) */
@@ -312,9 +324,7 @@ __global__ void __launch_bounds__(128, MINB)
                                 settle = true;
                         }
                 }
-                if (publish) {
-                        SF(F_LAT) = S.lat;
-                        SF(F_LON) = S.lon;
+                if (publish) { /* latitude and longitude are not part of a trace result */
                         SF(F_ALT) = S.alt;
                         SF(F_ELEV0) = S.elev0;
                         SF(F_ELEV1) = S.elev1;
@@ -324,8 +334,7 @@ __global__ void __launch_bounds__(128, MINB)
                 if (!settle) continue;
 
                 tb::Sample last;
-                last.lat = SF(F_LAT);
-                last.lon = SF(F_LON);
+                last.lat = last.lon = 0.;
                 last.alt = SF(F_ALT);
                 last.elev0 = SF(F_ELEV0);
                 last.elev1 = SF(F_ELEV1);
@@ -1356,6 +1365,33 @@ static enum turtle_return check_rule(turtle_function_t * fn, const struct turtle
         return TURTLE_RETURN_SUCCESS;
 }
 
+/* Launch one instance of the trace kernel. The shared-memory carve-out is asked to be
+ * just what the resident CTAs need: whatever they leave of the 256 kB is L1 for the DEM
+ * gathers (the default heuristic takes the next larger configuration). */
+template <bool LLA, bool PROJ, int MINB, int SHAPE>
+static void trace_start(const struct turtle_plan * plan, int per_sm, int blocks, int threads,
+    cudaStream_t stream, const TraceArgs & A)
+{
+        void (*kernel)(const tb::Geometry, const TraceArgs) = trace_kernel<LLA, PROJ, MINB, SHAPE>;
+        static int carveout_of[16] = { 0 };
+        const int key = per_sm & 15;
+        if (carveout_of[key] == 0) {
+                cudaFuncAttributes attr;
+                if (cudaFuncGetAttributes(&attr, kernel) == cudaSuccess) {
+                        const size_t need = (size_t)per_sm * (attr.sharedSizeBytes + 1024);
+                        int percent = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+                        if (percent > 100) percent = 100;
+                        carveout_of[key] = percent + 1;
+                } else {
+                        carveout_of[key] = 101;
+                }
+                cudaGetLastError();
+        }
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+            carveout_of[key] - 1);
+        kernel<<<blocks, threads, 0, stream>>>(plan->G, A);
+}
+
 static cudaError_t launch_trace(struct turtle_plan * plan, int slot, size_t n,
     const double * d_position, const double * d_direction,
     const struct turtle_trace_rule * rule, struct turtle_trace_result * d_results,
@@ -1384,21 +1420,23 @@ static cudaError_t launch_trace(struct turtle_plan * plan, int slot, size_t n,
 #define TRACE_LAUNCH(MINB)                                                             \
         do {                                                                           \
                 if (lla && proj)                                                       \
-                        trace_kernel<true, true, MINB><<<blocks, threads, 0, stream>>>(plan->G, A);   \
+                        trace_start<true, true, MINB, tb::SHAPE_GENERIC>(plan, per_sm, blocks, threads, stream, A); \
                 else if (lla)                                                          \
-                        trace_kernel<true, false, MINB><<<blocks, threads, 0, stream>>>(plan->G, A);  \
+                        trace_start<true, false, MINB, tb::SHAPE_GENERIC>(plan, per_sm, blocks, threads, stream, A); \
                 else if (proj)                                                         \
-                        trace_kernel<false, true, MINB><<<blocks, threads, 0, stream>>>(plan->G, A);  \
+                        trace_start<false, true, MINB, tb::SHAPE_GENERIC>(plan, per_sm, blocks, threads, stream, A); \
                 else                                                                   \
-                        trace_kernel<false, false, MINB><<<blocks, threads, 0, stream>>>(plan->G, A); \
+                        trace_start<false, false, MINB, tb::SHAPE_GENERIC>(plan, per_sm, blocks, threads, stream, A); \
         } while (0)
         /* the register budget follows the requested residency (in units of 128 threads) */
         const int minb = per_sm * threads / 128;
         if (plan->specialise && (tb::geometry_shape(plan->G) == tb::SHAPE_STACK)) {
                 if (minb <= 6)
-                        trace_kernel<false, false, 6, tb::SHAPE_STACK><<<blocks, threads, 0, stream>>>(plan->G, A);
+                        trace_start<false, false, 6, tb::SHAPE_STACK>(plan, per_sm, blocks, threads, stream, A);
+                else if (minb == 7)
+                        trace_start<false, false, 7, tb::SHAPE_STACK>(plan, per_sm, blocks, threads, stream, A);
                 else
-                        trace_kernel<false, false, 8, tb::SHAPE_STACK><<<blocks, threads, 0, stream>>>(plan->G, A);
+                        trace_start<false, false, 8, tb::SHAPE_STACK>(plan, per_sm, blocks, threads, stream, A);
         } else if (minb <= 4)
                 TRACE_LAUNCH(4);
         else if (minb == 5)
@@ -2089,6 +2127,55 @@ extern "C" enum turtle_return turtle_map_elevation_ecef_batch(struct turtle_map 
 }
 
 /* ---- FP64 peak ------------------------------------------------------------------------ */
+
+/* ---- peer memory (result delivery over NVLink, turtle_b200.h) ------------------- */
+
+extern "C" enum turtle_return turtle_b200_peer_alloc(size_t bytes, void ** device_pointer)
+{
+        *device_pointer = NULL;
+        enum turtle_return rc = require_current(FN(&turtle_b200_peer_alloc));
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        CUDA_TRY(&turtle_b200_peer_alloc, cudaMalloc(device_pointer, bytes ? bytes : 1));
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_b200_peer_free(void * device_pointer)
+{
+        if (device_pointer == NULL) return TURTLE_RETURN_SUCCESS;
+        CUDA_TRY(&turtle_b200_peer_free, cudaFree(device_pointer));
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_b200_peer_export(
+    void * device_pointer, unsigned char handle[TURTLE_B200_PEER_HANDLE_BYTES])
+{
+        static_assert(sizeof(cudaIpcMemHandle_t) == TURTLE_B200_PEER_HANDLE_BYTES,
+            "CUDA IPC handle size");
+        cudaIpcMemHandle_t h;
+        CUDA_TRY(&turtle_b200_peer_export, cudaIpcGetMemHandle(&h, device_pointer));
+        memcpy(handle, &h, sizeof h);
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_b200_peer_open(
+    const unsigned char handle[TURTLE_B200_PEER_HANDLE_BYTES], void ** device_pointer)
+{
+        *device_pointer = NULL;
+        enum turtle_return rc = require_current(FN(&turtle_b200_peer_open));
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle, sizeof h);
+        CUDA_TRY(&turtle_b200_peer_open,
+            cudaIpcOpenMemHandle(device_pointer, h, cudaIpcMemLazyEnablePeerAccess));
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_b200_peer_close(void * device_pointer)
+{
+        if (device_pointer == NULL) return TURTLE_RETURN_SUCCESS;
+        CUDA_TRY(&turtle_b200_peer_close, cudaIpcCloseMemHandle(device_pointer));
+        return TURTLE_RETURN_SUCCESS;
+}
 
 extern "C" double turtle_b200_dfma_peak(int repeats)
 {
