@@ -8,9 +8,8 @@
  * the reference tree). The implementation behind it is new;
  * batched, GPU-resident entry points are declared in turtle_b200.h.
  *
- * Not provided (outside the hot path, see DESIGN.md "out of scope"):
- * turtle_map_dump and turtle_map_load for PNG/GeoTIFF/GRD/ASC. turtle_map_load
- * accepts `.hgt` only.
+ * turtle_map_load reads the five formats of the reference (.hgt .png .tif .grd .asc)
+ * and turtle_map_dump writes .png and .tif, without libpng / libtiff (tb_io.cpp).
  */
 #ifndef TURTLE_H
 #define TURTLE_H
@@ -86,7 +85,9 @@ TURTLE_API enum turtle_return turtle_map_create(struct turtle_map ** map,
     const struct turtle_map_info * info, const char * projection);
 TURTLE_API void turtle_map_destroy(struct turtle_map ** map);
 TURTLE_API enum turtle_return turtle_map_load(
-    struct turtle_map ** map, const char * path); /* `.hgt` only */
+    struct turtle_map ** map, const char * path); /* .hgt .png .tif .grd .asc */
+TURTLE_API enum turtle_return turtle_map_dump(
+    const struct turtle_map * map, const char * path); /* .png .tif (ref: :423) */
 TURTLE_API enum turtle_return turtle_map_fill(
     struct turtle_map * map, int ix, int iy, double elevation);
 TURTLE_API enum turtle_return turtle_map_node(const struct turtle_map * map,

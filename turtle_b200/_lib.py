@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libturtle_b200.so")
+# (TURTLE_B200_LIB: development hook to A/B another build of the same library)
+LIB_PATH = os.environ.get("TURTLE_B200_LIB") or os.path.join(HERE, "libturtle_b200.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
@@ -60,6 +61,7 @@ SIGNATURES = {
     "turtle_map_create": (_I, [_PP, C.POINTER(MapInfo), C.c_char_p]),
     "turtle_map_destroy": (None, [_PP]),
     "turtle_map_load": (_I, [_PP, C.c_char_p]),
+    "turtle_map_dump": (_I, [_P, C.c_char_p]),
     "turtle_map_fill": (_I, [_P, _I, _I, _D]),
     "turtle_map_node": (_I, [_P, _I, _I, c_double_p, c_double_p, c_double_p]),
     "turtle_map_elevation": (_I, [_P, _D, _D, c_double_p, c_int_p]),

@@ -189,6 +189,10 @@ class Map:
         lib.turtle_map_meta(self._p, C.byref(info), C.byref(name))
         return info, (name.value.decode() if name.value else None)
 
+    def dump(self, path):
+        """turtle_map_dump: `.png` (any map) or `.tif` (integer metre scale, geodetic)."""
+        _check(lib.turtle_map_dump(self._p, path.encode()))
+
     def node(self, ix, iy):
         x, y, z = C.c_double(), C.c_double(), C.c_double()
         _check(lib.turtle_map_node(self._p, ix, iy, C.byref(x), C.byref(y), C.byref(z)))
@@ -230,7 +234,7 @@ class Map:
 
 
 class Stack:
-    """turtle_stack over a directory of `.hgt` tiles."""
+    """turtle_stack over a directory of tiles (.hgt .png .tif .grd .asc)."""
 
     def __init__(self, path, size=0):
         self._p = C.c_void_p()

@@ -11,6 +11,7 @@
  * format (tests/test-turtle.c:482-507) keep working.
  */
 #include "tb_host.hpp"
+#include "tb_io.hpp"
 #include "turtle_b200.h"
 
 #include <dirent.h>
@@ -375,106 +376,71 @@ extern "C" void turtle_map_destroy(struct turtle_map ** map)
         *map = NULL;
 }
 
-/* HGT naming, ref: io/hgt.c:61-104. Returns 0 on success. */
-static int hgt_parse_name(const char * path, int * nxy, double * x0, double * y0)
-{
-        const char * filename = path;
-        for (const char * p = path; *p != 0x0; p++)
-                if ((*p == '/') || (*p == '\\')) filename = p + 1;
-        if (strlen(filename) < 8) return -1;
-        *x0 = atoi(filename + 4);
-        if (filename[3] == 'W')
-                *x0 = -*x0;
-        else if (filename[3] != 'E')
-                return -1;
-        *y0 = atoi(filename + 1);
-        if (filename[0] == 'S')
-                *y0 = -*y0;
-        else if (filename[0] != 'N')
-                return -1;
-        const char * ext = NULL;
-        for (const char * p = filename + 7; *p != 0x0; p++)
-                if (*p == '.') ext = p + 1;
-        if (ext == NULL) return -1;
-        const int n = (int)(ext - filename) - 8;
-        if ((n == 0) || (strncmp(filename + 8, "SRTMGL1", n - 1) == 0))
-                *nxy = 3601;
-        else
-                *nxy = 1201;
-        return 0;
-}
-
-static const char * path_extension(const char * path)
-{
-        const char * ext = NULL;
-        for (const char * p = path; *p != 0x0; p++) {
-                if (*p == '.') ext = p + 1;
-                if ((*p == '/') || (*p == '\\')) ext = NULL;
-        }
-        return ext;
-}
-
-/* Load one `.hgt` tile: big-endian int16, rows NORTH first on disk
- * (ref: io/hgt.c:127-147); stored here south first, native endian. */
-static enum turtle_return map_load_hgt(struct turtle_map ** map, const char * path,
+/* ref: turtle_map_load_, map.c:116-158 + the io plug-ins (tb_io.cpp). Nodes are kept
+ * rows south first, native endian, whatever the file stored. */
+static enum turtle_return map_load_file(struct turtle_map ** map, const char * path,
     turtle_function_t * caller)
 {
-        static const char * HGT_C = "src/turtle/io/hgt.c";
         *map = NULL;
-        int nxy;
-        double x0, y0;
-        if (hgt_parse_name(path, &nxy, &x0, &y0) != 0)
-                return tbh::raise(caller, TURTLE_RETURN_BAD_FORMAT, HGT_C, __LINE__,
-                    "invalid hgt filename for `%s'", path);
-        FILE * fid = fopen(path, "rb");
-        if (fid == NULL)
-                return tbh::raise(caller, TURTLE_RETURN_PATH_ERROR, HGT_C, __LINE__,
-                    "could not open file `%s'", path);
-        struct turtle_map * m = map_alloc(nxy, nxy);
-        if (m == NULL) {
-                fclose(fid);
+        tbio::Header h;
+        tbio::RawLayout layout;
+        tbio::Error err;
+        std::vector<uint16_t> raw;
+        if (tbio::read_map(path, h, layout, raw, err) != 0)
+                return tbh::raise(caller, err.code, err.file, __LINE__, "%s", err.message.c_str());
+        struct turtle_projection proj;
+        char msg[256];
+        enum turtle_return rc = projection_parse(
+            &proj, h.projection.empty() ? NULL : h.projection.c_str(), msg, sizeof msg);
+        if (rc != TURTLE_RETURN_SUCCESS) return tbh::raise(caller, rc, PROJ_C, __LINE__, "%s", msg);
+        struct turtle_map * m = new (std::nothrow) turtle_map();
+        if (m == NULL)
                 return tbh::raise(caller, TURTLE_RETURN_MEMORY_ERROR, MAP_C, __LINE__,
                     "could not allocate memory for map `%s'", path);
-        }
-        std::vector<uint16_t> row(nxy);
-        for (int r = 0; r < nxy; r++) {
-                if (fread(row.data(), sizeof(uint16_t), nxy, fid) != (size_t)nxy) {
-                        fclose(fid);
-                        delete m;
-                        return tbh::raise(caller, TURTLE_RETURN_BAD_FORMAT, HGT_C,
-                            __LINE__, "missing data when reading file `%s'", path);
-                }
-                uint16_t * dst = m->nodes.data() + (size_t)(nxy - 1 - r) * nxy;
-                for (int i = 0; i < nxy; i++)
-                        dst[i] = (uint16_t)((row[i] << 8) | (row[i] >> 8));
-        }
-        fclose(fid);
-        m->x0 = x0;
-        m->y0 = y0;
-        m->z0 = -32767.;
-        m->dz = 1.;
-        m->dx = 1. / (nxy - 1);
-        m->dy = 1. / (nxy - 1);
-        m->kind = tb::NODE_DIRECT_I16;
-        m->projection.type = -1;
-        m->projection.tag[0] = 0x0;
-        strcpy(m->encoding, "none");
+        tbio::normalise(h, layout, raw);
+        m->nodes.swap(raw);
+        m->nx = h.nx;
+        m->ny = h.ny;
+        m->x0 = h.x0;
+        m->y0 = h.y0;
+        m->z0 = h.z0;
+        m->dx = h.dx;
+        m->dy = h.dy;
+        m->dz = h.dz;
+        m->kind = h.kind;
+        m->projection = proj;
+        m->stack = NULL;
+        m->version = 1;
+        snprintf(m->encoding, sizeof m->encoding, "%s", h.encoding.c_str());
         *map = m;
         return TURTLE_RETURN_SUCCESS;
 }
 
 extern "C" enum turtle_return turtle_map_load(struct turtle_map ** map, const char * path)
 {
-        static const char * IO_C = "src/turtle/io.c";
-        *map = NULL;
-        const char * ext = path_extension(path);
-        if (ext == NULL)
-                return RAISE(&turtle_map_load, TURTLE_RETURN_BAD_EXTENSION, IO_C,
-                    "no valid format for file `%s'", path);
-        if (strcmp(ext, "hgt") != 0)
-                return RAISE(&turtle_map_load, TURTLE_RETURN_BAD_EXTENSION, IO_C,
-                    "unsuported file format `%s'", ext);
-        return map_load_hgt(map, path, FN(&turtle_map_load));
+        return map_load_file(map, path, FN(&turtle_map_load));
+}
+
+/* ref: turtle_map_dump, map.c:160-176 (`.png` and `.tif` have writers) */
+extern "C" enum turtle_return turtle_map_dump(const struct turtle_map * map, const char * path)
+{
+        tbio::Header h;
+        h.nx = map->nx;
+        h.ny = map->ny;
+        h.x0 = map->x0;
+        h.y0 = map->y0;
+        h.z0 = map->z0;
+        h.dx = map->dx;
+        h.dy = map->dy;
+        h.dz = map->dz;
+        h.kind = map->kind;
+        const char * tag = turtle_projection_name(&map->projection);
+        h.projection = (tag != NULL) ? tag : "";
+        tbio::Error err;
+        if (tbio::write_map(path, h, map->nodes, err) != 0)
+                return tbh::raise(FN(&turtle_map_dump), err.code, err.file, __LINE__, "%s",
+                    err.message.c_str());
+        return TURTLE_RETURN_SUCCESS;
 }
 
 extern "C" enum turtle_return turtle_map_fill(
@@ -655,7 +621,7 @@ extern "C" enum turtle_return turtle_stack_create(struct turtle_stack ** stack,
                     "could not access %s", path);
 
         /* first pass: tile spans and bounding box (ref: stack.c:59-132) */
-        struct found { std::string path; double x0, y0; };
+        struct found { std::string path; double x0, y0; tb::MapDesc desc; };
         std::vector<found> files;
         double lat_min = DBL_MAX, long_min = DBL_MAX;
         double lat_max = -DBL_MAX, long_max = -DBL_MAX;
@@ -667,19 +633,18 @@ extern "C" enum turtle_return turtle_stack_create(struct turtle_stack ** stack,
                 std::string full = std::string(path) + "/" + entry->d_name;
                 struct stat st;
                 if ((stat(full.c_str(), &st) != 0) || S_ISDIR(st.st_mode)) continue;
-                const char * ext = path_extension(entry->d_name);
-                if ((ext == NULL) || (strcmp(ext, "hgt") != 0)) continue;
-                int nxy;
-                double x0, y0;
-                if (hgt_parse_name(full.c_str(), &nxy, &x0, &y0) != 0) {
+                /* any of the five formats makes a tile (stack.c:76-91) */
+                if (!tbio::known_extension(tbio::extension(entry->d_name))) continue;
+                tbio::Header th;
+                tbio::Error terr;
+                if (tbio::read_header(full.c_str(), th, terr) != 0) {
                         closedir(dir);
-                        return RAISE(&turtle_stack_create, TURTLE_RETURN_BAD_FORMAT,
-                            "src/turtle/io/hgt.c", "invalid hgt filename for `%s'",
-                            full.c_str());
+                        return tbh::raise(FN(&turtle_stack_create), terr.code, terr.file, __LINE__,
+                            "%s", terr.message.c_str());
                 }
-                const double tdx = 1. / (nxy - 1), tdy = 1. / (nxy - 1);
-                const double dx = tdx * (nxy - 1);
-                const double dy = tdy * (nxy - 1);
+                const double x0 = th.x0, y0 = th.y0;
+                const double dx = th.dx * (th.nx - 1);
+                const double dy = th.dy * (th.ny - 1);
                 if (long_delta == 0.)
                         long_delta = dx;
                 else if (long_delta != dx) {
@@ -698,7 +663,16 @@ extern "C" enum turtle_return turtle_stack_create(struct turtle_stack ** stack,
                 if (y0 < lat_min) lat_min = y0;
                 if (x0 + dx > long_max) long_max = x0 + dx;
                 if (y0 + dy > lat_max) lat_max = y0 + dy;
-                files.push_back({ full, x0, y0 });
+                tb::MapDesc desc;
+                memset(&desc, 0x0, sizeof desc);
+                desc.nx = th.nx;
+                desc.ny = th.ny;
+                desc.x0 = th.x0;
+                desc.y0 = th.y0;
+                desc.dx = th.dx;
+                desc.dy = th.dy;
+                tb::map_desc_finish(desc);
+                files.push_back({ full, x0, y0, desc });
         }
         closedir(dir);
         if (rc != TURTLE_RETURN_SUCCESS)
@@ -735,10 +709,14 @@ extern "C" enum turtle_return turtle_stack_create(struct turtle_stack ** stack,
         s->pinned = 0;
         s->path.assign((size_t)lat_n * long_n, std::string());
         s->tile.assign((size_t)lat_n * long_n, NULL);
+        tb::MapDesc none;
+        memset(&none, 0x0, sizeof none);
+        s->header.assign((size_t)lat_n * long_n, none);
         for (size_t i = 0; i < files.size(); i++) { /* ref: stack.c:187-190 */
                 const int ix = (int)((files[i].x0 - long_min) / long_delta);
                 const int iy = (int)((files[i].y0 - lat_min) / lat_delta);
                 s->path[(size_t)iy * long_n + ix] = files[i].path;
+                s->header[(size_t)iy * long_n + ix] = files[i].desc;
         }
         *stack = s;
         return TURTLE_RETURN_SUCCESS;
@@ -791,7 +769,7 @@ static enum turtle_return stack_load_cell(struct turtle_stack * stack, int cell,
 {
         if (stack->tile[cell] != NULL) return TURTLE_RETURN_SUCCESS;
         struct turtle_map * m;
-        enum turtle_return rc = map_load_hgt(&m, stack->path[cell].c_str(), caller);
+        enum turtle_return rc = map_load_file(&m, stack->path[cell].c_str(), caller);
         if (rc != TURTLE_RETURN_SUCCESS) return rc;
         if (stack->pinned == 0) {
                 while ((int)stack->mru.size() >= stack->max_size && !stack->mru.empty())
@@ -870,16 +848,9 @@ static enum turtle_return stack_elevation_scalar(struct turtle_stack * stack,
                         if (stack->path[cell].empty()) continue;
                         /* ownership only needs the tile meta: x0, y0, dx, nx */
                         if (stack->tile[cell] == NULL) {
-                                int nxy;
-                                double x0, y0;
-                                hgt_parse_name(stack->path[cell].c_str(), &nxy, &x0, &y0);
-                                tb::MapDesc d;
-                                d.nx = d.ny = nxy;
-                                d.x0 = x0;
-                                d.y0 = y0;
-                                d.dx = d.dy = 1. / (nxy - 1);
-                                tb::map_desc_finish(d);
-                                if (!tb::tile_owns(d, latitude, longitude)) continue;
+                                /* the header read by turtle_stack_create */
+                                if (!tb::tile_owns(stack->header[cell], latitude, longitude))
+                                        continue;
                                 enum turtle_return rc = stack_load_cell(stack, cell, caller);
                                 if (rc != TURTLE_RETURN_SUCCESS) {
                                         *elevation = 0.;
@@ -1516,6 +1487,7 @@ extern "C" const char * turtle_error_function(turtle_function_t * caller)
         NAME(turtle_map_fill);
         NAME(turtle_map_gradient);
         NAME(turtle_map_load);
+        NAME(turtle_map_dump);
         NAME(turtle_map_meta);
         NAME(turtle_map_node);
         NAME(turtle_map_projection);

@@ -56,6 +56,8 @@ struct turtle_stack {
         std::string root;
         std::vector<std::string> path;        /* per cell, empty = no file */
         std::vector<struct turtle_map *> tile; /* per cell, NULL = not loaded */
+        std::vector<tb::MapDesc> header;       /* per cell: shape and origin from the file
+                                                * header (no nodes), read once at creation */
         std::vector<int> mru;                  /* loaded cells, most recent first */
         int pinned;                            /* > 0: residency plans hold the tiles */
 };
