@@ -101,6 +101,42 @@ struct turtle_plan_counters {
  * nothing: the plan owns device copies. */
 TURTLE_API enum turtle_return turtle_stepper_freeze(
     struct turtle_stepper * stepper, int device, struct turtle_plan ** plan);
+
+/* ---- residency planning for stacks larger than one GPU -----------------------------
+ * A world-scale stack (14 k SRTMGL1 tiles, 370 GB) does not fit 180 GB of HBM and the
+ * device has no on-demand cache. The plan is made for a REGION instead: only the tiles
+ * whose footprint meets the box become resident; the others answer `outside`, exactly as
+ * a missing tile does. NaN bounds are open. turtle_residency_from_rays derives the box
+ * from the rays to be traced and their stop rule (see there).
+ *
+ * Tiles that are not already loaded on the host are INGESTED ON THE DEVICE: their file is
+ * read (any of .hgt .png .tif .grd .asc), the nodes are copied in FILE order and a kernel
+ * converts byte order and row order straight into the tile pool -- no host-side copy of
+ * the stack is ever built (turtle_stepper_freeze does the same). */
+struct turtle_residency {
+        double latitude_min, latitude_max, longitude_min, longitude_max;
+        size_t memory_limit; /* refuse plans above this many bytes of HBM; 0 = what is free */
+};
+struct turtle_residency_report {
+        uint64_t tiles_resident; /* stack tiles uploaded */
+        uint64_t tiles_skipped;  /* stack tiles with a file, left out by the region */
+        uint64_t tiles_ingested; /* ... of the resident ones, decoded on the device */
+        uint64_t bytes;          /* HBM held by the plan */
+        double read_ms, upload_ms; /* file reading / parsing, copies + ingest kernels */
+};
+TURTLE_API enum turtle_return turtle_stepper_freeze_region(
+    struct turtle_stepper * stepper, int device, const struct turtle_residency * region,
+    struct turtle_plan ** plan);
+TURTLE_API void turtle_plan_residency_get(
+    const struct turtle_plan * plan, struct turtle_residency_report * report);
+/* Geodetic bounding box of the ground tracks of n rays (host arrays [n][3]), each followed
+ * until the stop rule must have ended it: min(rule->length_max, the chord to the sphere of
+ * radius a + rule->altitude_max), sampled every `step` metres (<= 0: 1000 m), and widened
+ * by `margin` degrees. Conservative for rays that stop on leaving the data set. Rays
+ * through a pole or across the date line open the longitude bounds (NaN). */
+TURTLE_API enum turtle_return turtle_residency_from_rays(size_t n, const double * position,
+    const double * direction, const struct turtle_trace_rule * rule, double step,
+    double margin, struct turtle_residency * region);
 TURTLE_API void turtle_plan_destroy(struct turtle_plan ** plan);
 TURTLE_API int turtle_plan_device(const struct turtle_plan * plan);
 /* Bytes of HBM held by the plan (tiles + tables). */
@@ -123,6 +159,12 @@ TURTLE_API void turtle_plan_schedule_set(struct turtle_plan * plan, int mode);
  * stepper_sample (stepper.c:717-743) resolved at compile time. 0: always the generic
  * kernel. Results are byte-identical (tests/test_gpu_trace.py); only the time differs. */
 TURTLE_API void turtle_plan_specialise_set(struct turtle_plan * plan, int enable);
+/* How the host-pointer call turtle_stepper_trace_batch overlaps its copies with the
+ * stepping. 0 (default): streamed -- one persistent kernel over the whole batch, fed and
+ * drained by the copy engines in 512 Ki-ray pieces (lanes wait for their ray, finished
+ * chunks are copied back as they complete). 1: chunked -- one kernel per 1 Mi-ray chunk on
+ * three streams (also used whenever a ray schedule is set). Results are identical. */
+TURTLE_API void turtle_plan_pipeline_set(struct turtle_plan * plan, int mode);
 
 /* ---- whole rays: reset, query, then step until the rule stops the ray ------ */
 TURTLE_API enum turtle_return turtle_stepper_trace_batch(

@@ -156,6 +156,10 @@ def test_determinism_and_chunking(small_stack):
     c = plan.trace(pos, dirs, rule)
     assert a.tobytes() == c.tobytes()
     plan.schedule_set(0)
+    plan.pipeline_set(1)    # one kernel per chunk instead of the streamed single kernel
+    c = plan.trace(pos, dirs, rule)
+    assert a.tobytes() == c.tobytes()
+    plan.pipeline_set(0)
     plan.specialise_set(0)  # generic list-walking kernel instead of the single-stack one
     c = plan.trace(pos, dirs, rule)
     assert a.tobytes() == c.tobytes()

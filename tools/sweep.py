@@ -45,6 +45,9 @@ def main():
             plan.trace_device(n, d_pos, d_dir, rule, d_res)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 3
+        if os.environ.get("SWEEP_SKIP_HOST"):
+            print(json.dumps(dict(order=order, special=special, ctas_per_sm=c, device_ms=round(ms, 2))), flush=True)
+            continue
         plan.trace(h_pos.numpy(), h_dir.numpy(), rule, results=res_np)
         t0 = time.perf_counter()
         for _ in range(2):

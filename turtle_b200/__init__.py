@@ -8,4 +8,4 @@ from .api import (Map, Plan, Projection, Stack, States, Stepper, TurtleError,  #
                   TRACE_RESULT, device_count, dfma_peak, ecef_from_geodetic,
                   ecef_from_geodetic_batch, ecef_from_horizontal,
                   ecef_from_horizontal_batch, ecef_to_geodetic, ecef_to_geodetic_batch,
-                  trace_rule)
+                  trace_rule, residency_from_rays)

@@ -29,6 +29,20 @@ class TraceRule(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class Residency(C.Structure):
+    """struct turtle_residency (include/turtle_b200.h)."""
+    _fields_ = [("latitude_min", C.c_double), ("latitude_max", C.c_double),
+                ("longitude_min", C.c_double), ("longitude_max", C.c_double),
+                ("memory_limit", C.c_size_t)]
+
+
+class ResidencyReport(C.Structure):
+    """struct turtle_residency_report (include/turtle_b200.h)."""
+    _fields_ = [("tiles_resident", C.c_uint64), ("tiles_skipped", C.c_uint64),
+                ("tiles_ingested", C.c_uint64), ("bytes", C.c_uint64),
+                ("read_ms", C.c_double), ("upload_ms", C.c_double)]
+
+
 class PlanCounters(C.Structure):
     """struct turtle_plan_counters (include/turtle_b200.h)."""
     _fields_ = [("rays", C.c_uint64), ("steps", C.c_uint64),
@@ -113,6 +127,11 @@ SIGNATURES = {
     "turtle_plan_launch_set": (None, [_P, _I, _I]),
     "turtle_plan_schedule_set": (None, [_P, _I]),
     "turtle_plan_specialise_set": (None, [_P, _I]),
+    "turtle_plan_pipeline_set": (None, [_P, _I]),
+    "turtle_stepper_freeze_region": (_I, [_P, _I, C.POINTER(Residency), _PP]),
+    "turtle_plan_residency_get": (None, [_P, C.POINTER(ResidencyReport)]),
+    "turtle_residency_from_rays": (_I, [_N, _P, _P, C.POINTER(TraceRule), C.c_double,
+                                        C.c_double, C.POINTER(Residency)]),
     # peer memory
     "turtle_b200_peer_alloc": (_I, [_N, _PP]),
     "turtle_b200_peer_free": (_I, [_P]),

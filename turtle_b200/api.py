@@ -9,7 +9,8 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import (ERROR_HANDLER, MapInfo, PlanCounters, TraceRule, lib)
+from ._lib import (ERROR_HANDLER, MapInfo, PlanCounters, Residency, ResidencyReport, TraceRule,
+                   lib)
 
 TRACE_RESULT = np.dtype([
     ("position", "<f8", (3,)), ("altitude", "<f8"), ("length", "<f8", (4,)),
@@ -316,12 +317,24 @@ class Stepper:
                     altitude=al.value, elevation=(el[0], el[1]), step=st.value,
                     index=(idx[0], idx[1]))
 
-    def freeze(self, device=0):
-        return Plan(self, device)
+    def freeze(self, device=0, region=None, memory_limit=0):
+        """Residency plan on `device`. ``region`` = (lat_min, lat_max, lon_min, lon_max)
+        (None / NaN = open) or a Residency from ``residency_from_rays``: only the stack
+        tiles that meet it are uploaded (turtle_stepper_freeze_region)."""
+        return Plan(self, device, region, memory_limit)
 
     def __del__(self):
         if getattr(self, "_p", None):
             lib.turtle_stepper_destroy(C.byref(self._p))
+
+
+def residency_from_rays(position, direction, rule, step=1000., margin=0.):
+    """Bounding box (a Residency) of the ground tracks of the rays under `rule`."""
+    position, direction = _f8(position, (-1, 3)), _f8(direction, (-1, 3))
+    r = Residency()
+    _check(lib.turtle_residency_from_rays(len(position), _ptr(position), _ptr(direction),
+                                          C.byref(rule), step, margin, C.byref(r)))
+    return r
 
 
 def trace_rule(altitude_max, altitude_min=-1.7976931348623157e308,
@@ -332,10 +345,26 @@ def trace_rule(altitude_max, altitude_min=-1.7976931348623157e308,
 class Plan:
     """turtle_plan: a stepper geometry resident on one GPU."""
 
-    def __init__(self, stepper, device=0):
+    def __init__(self, stepper, device=0, region=None, memory_limit=0):
         self._p = C.c_void_p()
         self.stepper = stepper
-        _check(lib.turtle_stepper_freeze(stepper.handle, device, C.byref(self._p)))
+        if region is None and not memory_limit:
+            _check(lib.turtle_stepper_freeze(stepper.handle, device, C.byref(self._p)))
+            return
+        if not isinstance(region, Residency):
+            nan = float("nan")
+            box = [nan if v is None else float(v) for v in (region or (None,) * 4)]
+            region = Residency(box[0], box[1], box[2], box[3], 0)
+        region.memory_limit = int(memory_limit)
+        _check(lib.turtle_stepper_freeze_region(stepper.handle, device, C.byref(region),
+                                                C.byref(self._p)))
+
+    def residency(self):
+        r = ResidencyReport()
+        lib.turtle_plan_residency_get(self._p, C.byref(r))
+        return dict(tiles_resident=r.tiles_resident, tiles_skipped=r.tiles_skipped,
+                    tiles_ingested=r.tiles_ingested, bytes=r.bytes, read_ms=r.read_ms,
+                    upload_ms=r.upload_ms)
 
     @property
     def handle(self):
@@ -354,6 +383,9 @@ class Plan:
 
     def schedule_set(self, mode):
         lib.turtle_plan_schedule_set(self._p, mode)
+
+    def pipeline_set(self, mode):
+        lib.turtle_plan_pipeline_set(self._p, int(mode))
 
     def specialise_set(self, enable):
         lib.turtle_plan_specialise_set(self._p, int(enable))

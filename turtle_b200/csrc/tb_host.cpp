@@ -671,6 +671,10 @@ extern "C" enum turtle_return turtle_stack_create(struct turtle_stack ** stack,
                 desc.y0 = th.y0;
                 desc.dx = th.dx;
                 desc.dy = th.dy;
+                desc.z0 = th.z0;
+                desc.dz = th.dz;
+                desc.kind = th.kind;
+                desc.pitch = th.nx;
                 tb::map_desc_finish(desc);
                 files.push_back({ full, x0, y0, desc });
         }
@@ -1227,11 +1231,39 @@ enum turtle_return tbh::stepper_flatten(struct turtle_stepper * s,
                 s->flat.G.resolution = s->resolution_factor;
                 return TURTLE_RETURN_SUCCESS;
         }
+        enum turtle_return rc = tbh::flatten_into(s, s->flat, caller, 1, NULL);
+        if (rc == TURTLE_RETURN_SUCCESS) s->dirty = 0;
+        return rc;
+}
+
+/* Does the closed footprint of a tile meet the region of a residency plan? */
+static int tile_in_region(const tb::MapDesc & t, const struct turtle_residency * r)
+{
+        if (r == NULL) return 1;
+        const double x1 = t.x0 + t.dx * t.nx1, y1 = t.y0 + t.dy * t.ny1;
+        if (!isnan(r->longitude_min) && (x1 < r->longitude_min)) return 0;
+        if (!isnan(r->longitude_max) && (t.x0 > r->longitude_max)) return 0;
+        if (!isnan(r->latitude_min) && (y1 < r->latitude_min)) return 0;
+        if (!isnan(r->latitude_max) && (t.y0 > r->latitude_max)) return 0;
+        return 1;
+}
+
+/* Flatten the lists into tb::Geometry.
+ *   load_tiles = 1: every tile of every stack is made resident on the HOST and the
+ *                   descriptors point to host nodes (the scalar turtle.h calls);
+ *   load_tiles = 0: residency plan of a device -- tiles that are not on the host are
+ *                   described from their file header only (F.src NULL, F.file set: the
+ *                   freeze ingests them on the device), and tiles outside `region` are
+ *                   left out of the plan (they answer `outside`). */
+enum turtle_return tbh::flatten_into(struct turtle_stepper * s, tb_flat_geometry & F,
+    turtle_function_t * caller, int load_tiles, const struct turtle_residency * region)
+{
         std::lock_guard<std::mutex> guard(g_residency_mutex);
-        tb_flat_geometry & F = s->flat;
         F.maps.clear();
         F.src.clear();
+        F.file.clear();
         F.tiles.clear();
+        F.skipped = 0;
         tb::Geometry & G = F.G;
         memset(&G, 0x0, sizeof(G));
 
@@ -1265,13 +1297,16 @@ enum turtle_return tbh::stepper_flatten(struct turtle_stepper * s,
                         G.data[i].ref = (int)F.maps.size();
                         F.maps.push_back(map_desc(d.map));
                         F.src.push_back(d.map);
+                        F.file.push_back(std::string());
                 } else if (d.kind == tb::DATA_STACK) {
                         struct turtle_stack * st = d.stack;
-                        st->pinned++;
-                        enum turtle_return rc = tbh::stack_load_all(st, caller);
-                        if (rc != TURTLE_RETURN_SUCCESS) {
-                                st->pinned--;
-                                return rc;
+                        if (load_tiles) {
+                                st->pinned++;
+                                enum turtle_return rc = tbh::stack_load_all(st, caller);
+                                if (rc != TURTLE_RETURN_SUCCESS) {
+                                        st->pinned--;
+                                        return rc;
+                                }
                         }
                         tb::StackDesc & S = G.stacks[G.n_stacks];
                         G.data[i].ref = G.n_stacks++;
@@ -1285,24 +1320,34 @@ enum turtle_return tbh::stepper_flatten(struct turtle_stepper * s,
                         S.nlon = st->longitude_n;
                         S.tile0 = (int)F.tiles.size();
                         const tb::TileRec none = { NULL, 0., 0., -1, 0 };
-                        const struct turtle_map * first = NULL;
+                        const tb::MapDesc * first = NULL;
+                        std::vector<tb::MapDesc> shapes(st->tile.size());
                         S.uniform = 1;
                         for (size_t c = 0; c < st->tile.size(); c++) {
                                 const struct turtle_map * t = st->tile[c];
-                                if (t == NULL) {
+                                if ((t == NULL) && (load_tiles || st->path[c].empty())) {
                                         F.tiles.push_back(none);
                                         continue;
                                 }
-                                const tb::TileRec rec = { t->nodes.data(), t->x0, t->y0,
-                                        (int)F.maps.size(), 0 };
+                                /* a tile on the host is described by its map, else by
+                                 * the header turtle_stack_create read from its file */
+                                shapes[c] = (t != NULL) ? map_desc(t) : st->header[c];
+                                if (!tile_in_region(shapes[c], region)) {
+                                        F.tiles.push_back(none);
+                                        F.skipped++;
+                                        continue;
+                                }
+                                const tb::TileRec rec = { shapes[c].nodes, shapes[c].x0,
+                                        shapes[c].y0, (int)F.maps.size(), 0 };
                                 F.tiles.push_back(rec);
-                                F.maps.push_back(map_desc(t));
+                                F.maps.push_back(shapes[c]);
                                 F.src.push_back(st->tile[c]);
-                                if (first == NULL) first = t;
-                                if ((t->nx != first->nx) || (t->ny != first->ny) ||
-                                    (t->dx != first->dx) || (t->dy != first->dy) ||
-                                    (t->z0 != first->z0) || (t->dz != first->dz) ||
-                                    (t->kind != first->kind))
+                                F.file.push_back((t != NULL) ? std::string() : st->path[c]);
+                                if (first == NULL) first = &shapes[c];
+                                if ((shapes[c].nx != first->nx) || (shapes[c].ny != first->ny) ||
+                                    (shapes[c].dx != first->dx) || (shapes[c].dy != first->dy) ||
+                                    (shapes[c].z0 != first->z0) || (shapes[c].dz != first->dz) ||
+                                    (shapes[c].kind != first->kind))
                                         S.uniform = 0;
                         }
                         if (first != NULL) {
@@ -1330,8 +1375,8 @@ enum turtle_return tbh::stepper_flatten(struct turtle_stepper * s,
                         /* do all tiles cover exactly their grid cell? (tb::stack_elevation) */
                         S.aligned = (S.dlat > 0.) && (S.dlon > 0.) && !st->tile.empty();
                         for (size_t c = 0; S.aligned && (c < st->tile.size()); c++) {
-                                const struct turtle_map * t = st->tile[c];
-                                if (t == NULL) continue;
+                                if (F.tiles[S.tile0 + c].map < 0) continue;
+                                const tb::MapDesc * t = &shapes[c];
                                 const double ix = (double)(c % (size_t)S.nlon);
                                 const double iy = (double)(c / (size_t)S.nlon);
                                 const double tol = 1E-09;
@@ -1348,6 +1393,7 @@ enum turtle_return tbh::stepper_flatten(struct turtle_stepper * s,
                 G.geoid = (int)F.maps.size();
                 F.maps.push_back(map_desc(s->geoid));
                 F.src.push_back(s->geoid);
+                F.file.push_back(std::string());
         }
 
         int first = 0;
@@ -1365,7 +1411,6 @@ enum turtle_return tbh::stepper_flatten(struct turtle_stepper * s,
         G.n_metas = first;
         G.maps = F.maps.data();
         G.tiles = F.tiles.data();
-        s->dirty = 0;
         return TURTLE_RETURN_SUCCESS;
 }
 

@@ -14,6 +14,7 @@
 
 #include "tb_core.cuh"
 #include "turtle.h"
+#include "turtle_b200.h"
 
 /* Mirror of a map on one CUDA device (created lazily by the batch calls). */
 struct tb_device_mirror {
@@ -89,8 +90,10 @@ struct tb_stepper_transform {
 struct tb_flat_geometry {
         tb::Geometry G;
         std::vector<tb::MapDesc> maps;        /* nodes point to HOST memory */
-        std::vector<struct turtle_map *> src; /* the map behind each descriptor */
+        std::vector<struct turtle_map *> src; /* the map behind each descriptor, or NULL: */
+        std::vector<std::string> file;        /* ... the tile file to ingest on the device */
         std::vector<tb::TileRec> tiles;
+        size_t skipped = 0;                   /* tiles left out by the residency region */
 };
 
 /* ref: struct turtle_stepper, stepper.h:101-110 */
@@ -121,6 +124,9 @@ enum turtle_return stack_load_all(struct turtle_stack * stack,
 /* (Re)build stepper->flat. Loads every tile of every stack. */
 enum turtle_return stepper_flatten(struct turtle_stepper * stepper,
     turtle_function_t * caller);
+/* Flatten into `F`, for the host (load_tiles) or for a device residency plan. */
+enum turtle_return flatten_into(struct turtle_stepper * stepper, tb_flat_geometry & F,
+    turtle_function_t * caller, int load_tiles, const struct turtle_residency * region);
 
 void projection_to_desc(const struct turtle_projection * p, tb::ProjDesc * d);
 

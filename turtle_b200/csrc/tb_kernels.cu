@@ -24,7 +24,10 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
+#include <float.h>
 
 #include <algorithm>
 #include <map>
@@ -33,6 +36,7 @@
 #include <vector>
 
 #include "tb_host.hpp"
+#include "tb_io.hpp"
 #include "turtle_b200.h"
 
 #define FN(f) ((turtle_function_t *)(f))
@@ -54,7 +58,8 @@ static const char * BATCH_CU = "turtle_b200/csrc/tb_kernels.cu";
 namespace {
 
 enum { MODE_IDLE = 0, MODE_INIT = 1, MODE_TENT = 2, MODE_BISECT = 3, MODE_REBUILD = 4,
-       MODE_FINISH = 5 };
+       MODE_FINISH = 5,
+       MODE_WAIT = 6 /* holds a queue ticket whose ray has not arrived on the device yet */ };
 
 struct TraceArgs {
         unsigned long long n;
@@ -65,7 +70,52 @@ struct TraceArgs {
         unsigned long long * cursor; /* [0] next ray, [1] steps, [2] samples */
         double altitude_min, altitude_max, length_max;
         int max_steps;
+        /* streaming (host-pointer calls, see trace_streamed): rays [0, *watermark) have
+         * arrived; chunk_done[k] counts the finished rays of chunk k = ray >> chunk_shift.
+         * NULL: everything is resident, nothing is counted. */
+        int chunk_shift;
+        const unsigned long long * watermark;
+        unsigned * chunk_done;
 };
+
+#define STREAM_ABORT (~0ull)
+
+/* A ray's record is complete: it must be visible before it is counted for its chunk.
+ * The fence that guarantees it stalls the whole warp, so the count is deferred: the lane
+ * remembers the chunk (`owed`) and the warp settles its debts every 32 iterations with
+ * ONE fence (and when it exits). A lane that still owes a count when it finishes another
+ * ray settles at once. */
+__device__ __forceinline__ void record_done(const TraceArgs & A, unsigned long long ray,
+    int & owed)
+{
+        if (A.chunk_done != NULL) {
+                if (owed >= 0) {
+                        __threadfence();
+                        atomicAdd(A.chunk_done + owed, 1u);
+                }
+                owed = (int)(ray >> A.chunk_shift);
+        }
+}
+
+__device__ __forceinline__ void settle_done(const TraceArgs & A, int & owed)
+{
+        if (A.chunk_done == NULL) return;
+        if (__any_sync(0xffffffffu, owed >= 0)) {
+                __threadfence();
+                if (owed >= 0) atomicAdd(A.chunk_done + owed, 1u);
+                owed = -1;
+        }
+}
+
+/* Stream-ordered wait for a chunk of results (one thread): the copy that follows it in
+ * the stream finds every record of the chunk in place. */
+__global__ void wait_chunk_kernel(const unsigned * done, unsigned count,
+    const unsigned long long * watermark)
+{
+        const volatile unsigned * d = done;
+        const volatile unsigned long long * w = watermark;
+        while ((*d < count) && (*w != STREAM_ABORT)) __nanosleep(2000);
+}
 
 __device__ __forceinline__ bool finite3(const double v[3])
 {
@@ -100,7 +150,7 @@ __device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory")
 
 /* The persistent ray-tracing kernel. MINB = CTAs of 128 threads per SM the register
  * allocation is bounded for (occupancy vs registers is a measured trade). */
-template <bool LLA, bool PROJ, int MINB, int SHAPE = tb::SHAPE_GENERIC>
+template <bool LLA, bool PROJ, int MINB, int SHAPE = tb::SHAPE_GENERIC, bool STREAM = false>
 __global__ void __launch_bounds__(128, MINB)
     trace_kernel(const __grid_constant__ tb::Geometry G, const TraceArgs A)
 {
@@ -117,12 +167,20 @@ __global__ void __launch_bounds__(128, MINB)
         tb::LlaState lla[LLA ? tb::MAX_TRANSFORMS : 1];
         unsigned my_steps = 0u, my_samples = 0u;
         bool exhausted = false;
+        bool pending_wait = false; /* warp uniform: some lane holds a ticket */
+        int owed = -1;             /* chunk whose completion count this lane still owes */
+        unsigned iteration = 0u;
 
         for (;;) {
-                /* ---- refill idle lanes from the global ray queue ---------- */
+                if (STREAM && ((++iteration & 31u) == 0u)) settle_done(A, owed);
+                /* ---- refill idle lanes from the global ray queue ----------
+                 * An idle lane takes a ticket q (one atomicAdd per warp, ballot / popc
+                 * ranks) and WAITs until ray q is on the device: at once when the whole
+                 * batch is resident, else when the copy stream has moved the watermark
+                 * past q -- the other lanes of the warp keep stepping meanwhile. */
                 const unsigned idle = __ballot_sync(FULL, mode == MODE_IDLE);
-                if (idle != 0u) {
-                        if (!exhausted) {
+                if ((idle != 0u) || (STREAM && pending_wait)) {
+                        if ((idle != 0u) && !exhausted) {
                                 const int need = __popc(idle);
                                 unsigned long long base = 0ull;
                                 if (lane == 0u)
@@ -132,61 +190,95 @@ __global__ void __launch_bounds__(128, MINB)
                                         const unsigned rank = __popc(idle & ((1u << lane) - 1u));
                                         const unsigned long long q = base + rank;
                                         if (q < A.n) {
-                                                const unsigned long long r =
-                                                    (A.order != NULL) ? A.order[q] : q;
-                                                const double * p = A.position + 3ull * r;
-                                                const double * d = A.direction + 3ull * r;
-                                                const double pos[3] = { p[0], p[1], p[2] };
-                                                const double dir[3] = { d[0], d[1], d[2] };
-                                                SF(F_POS) = pos[0];
-                                                SF(F_POS + 1) = pos[1];
-                                                SF(F_POS + 2) = pos[2];
-                                                SF(F_DIR) = dir[0];
-                                                SF(F_DIR + 1) = dir[1];
-                                                SF(F_DIR + 2) = dir[2];
-#pragma unroll
-                                                for (int m = 0; m < TURTLE_TRACE_MEDIA; m++)
-                                                        SF(F_LEN + m) = 0.;
-                                                SF(F_TOTAL) = 0.;
-                                                SI(I_NSTEPS) = 0;
-                                                SI(I_NCHANGES) = 0;
-                                                SI(I_RAYLO) = (int)(unsigned)(r & 0xffffffffull);
-                                                SI(I_RAYHI) = (int)(unsigned)(r >> 32);
-                                                if (LLA) SI(I_PEND) = 0;
-                                                mode = MODE_INIT;
-                                                /* every ray starts from a reset stepper
-                                                 * (turtle_stepper_reset, stepper.c:647-651) */
-                                                if (LLA) {
-                                                        SF(F_LASTPOS) = SF(F_LASTPOS + 1) =
-                                                            SF(F_LASTPOS + 2) = DBL_MAX;
-                                                        tb::lla_reset(lla, G.n_transforms);
-                                                }
-                                                if (!finite3(pos) || !finite3(dir)) {
-                                                        turtle_trace_result * R = A.results + r;
-                                                        R->position[0] = pos[0];
-                                                        R->position[1] = pos[1];
-                                                        R->position[2] = pos[2];
-                                                        R->altitude = 0.;
-                                                        R->length[0] = R->length[1] = 0.;
-                                                        R->length[2] = R->length[3] = 0.;
-                                                        R->total = 0.;
-                                                        R->n_steps = 0;
-                                                        R->status = TURTLE_TRACE_INVALID;
-                                                        R->index[0] = R->index[1] = -1;
-                                                        R->medium_hash = 0u;
-                                                        R->n_changes = 0;
-                                                        mode = MODE_IDLE;
-                                                }
+                                                SI(I_RAYLO) = (int)(unsigned)(q & 0xffffffffull);
+                                                SI(I_RAYHI) = (int)(unsigned)(q >> 32);
+                                                mode = MODE_WAIT;
                                         }
                                 }
                                 if (base + (unsigned long long)need >= A.n) exhausted = true;
                         }
-                        if (__all_sync(FULL, mode == MODE_IDLE)) {
-                                if (exhausted) break;
+                        if (mode == MODE_WAIT) {
+                                const unsigned long long q =
+                                    ((unsigned long long)(unsigned)SI(I_RAYHI) << 32) |
+                                    (unsigned long long)(unsigned)SI(I_RAYLO);
+                                bool arrived = true;
+                                if (STREAM) {
+                                        const unsigned long long w =
+                                            *(const volatile unsigned long long *)A.watermark;
+                                        arrived = q < w;
+                                        if (w == STREAM_ABORT) mode = MODE_IDLE; /* host gave up */
+                                }
+                                if (arrived && (mode == MODE_WAIT)) {
+                                        const unsigned long long r =
+                                            (A.order != NULL) ? A.order[q] : q;
+                                        /* (L2 loads: a streamed ray has just been written by
+                                         * a copy engine, L1 must not serve an older line) */
+                                        const double * p = A.position + 3ull * r;
+                                        const double * d = A.direction + 3ull * r;
+                                        const double pos[3] = { __ldcg(p), __ldcg(p + 1),
+                                                __ldcg(p + 2) };
+                                        const double dir[3] = { __ldcg(d), __ldcg(d + 1),
+                                                __ldcg(d + 2) };
+                                        SF(F_POS) = pos[0];
+                                        SF(F_POS + 1) = pos[1];
+                                        SF(F_POS + 2) = pos[2];
+                                        SF(F_DIR) = dir[0];
+                                        SF(F_DIR + 1) = dir[1];
+                                        SF(F_DIR + 2) = dir[2];
+#pragma unroll
+                                        for (int m = 0; m < TURTLE_TRACE_MEDIA; m++)
+                                                SF(F_LEN + m) = 0.;
+                                        SF(F_TOTAL) = 0.;
+                                        SI(I_NSTEPS) = 0;
+                                        SI(I_NCHANGES) = 0;
+                                        SI(I_RAYLO) = (int)(unsigned)(r & 0xffffffffull);
+                                        SI(I_RAYHI) = (int)(unsigned)(r >> 32);
+                                        if (LLA) SI(I_PEND) = 0;
+                                        mode = MODE_INIT;
+                                        /* every ray starts from a reset stepper
+                                         * (turtle_stepper_reset, stepper.c:647-651) */
+                                        if (LLA) {
+                                                SF(F_LASTPOS) = SF(F_LASTPOS + 1) =
+                                                    SF(F_LASTPOS + 2) = DBL_MAX;
+                                                tb::lla_reset(lla, G.n_transforms);
+                                        }
+                                        if (!finite3(pos) || !finite3(dir)) {
+                                                turtle_trace_result * R = A.results + r;
+                                                R->position[0] = pos[0];
+                                                R->position[1] = pos[1];
+                                                R->position[2] = pos[2];
+                                                R->altitude = 0.;
+                                                R->length[0] = R->length[1] = 0.;
+                                                R->length[2] = R->length[3] = 0.;
+                                                R->total = 0.;
+                                                R->n_steps = 0;
+                                                R->status = TURTLE_TRACE_INVALID;
+                                                R->index[0] = R->index[1] = -1;
+                                                R->medium_hash = 0u;
+                                                R->n_changes = 0;
+                                                if (STREAM) record_done(A, r, owed);
+                                                mode = MODE_IDLE;
+                                        }
+                                }
+                        }
+                        if (STREAM) {
+                                const unsigned waiting = __ballot_sync(FULL, mode == MODE_WAIT);
+                                const unsigned resting = __ballot_sync(FULL, mode == MODE_IDLE);
+                                pending_wait = waiting != 0u;
+                                if ((waiting | resting) == FULL) { /* no lane has a ray */
+                                        settle_done(A, owed);
+                                        if (waiting != 0u)
+                                                __nanosleep(500);
+                                        else if (exhausted)
+                                                break;
+                                        continue;
+                                }
+                        } else if (__all_sync(FULL, mode == MODE_IDLE)) {
+                                if (exhausted) break; /* (a resident ray never waits) */
                                 continue;
                         }
                 }
-                if (mode == MODE_IDLE) continue;
+                if ((mode == MODE_IDLE) || (mode == MODE_WAIT)) continue;
 
                 /* ---- exactly one ECEF -> geodetic transform per lane and iteration:
                  * the one of a geometry sample, or -- local approximation on -- one of
@@ -389,6 +481,7 @@ __global__ void __launch_bounds__(128, MINB)
                         R->index[1] = last.idx1;
                         R->medium_hash = (unsigned)SI(I_HASH);
                         R->n_changes = SI(I_NCHANGES);
+                        if (STREAM) record_done(A, ray, owed);
                         mode = MODE_IDLE;
                 } else {
                         SI(I_MEDIUM0) = last.idx0;
@@ -957,6 +1050,25 @@ __global__ void __launch_bounds__(256) map_elevation_ecef_kernel(const tb::MapDe
         }
 }
 
+/* Device-side tile ingestion: `raw` holds the nodes of one tile in FILE order (row 0 is
+ * the northernmost when north_first, samples big-endian when big_endian); they are
+ * written to the tile pool rows south first, native endian, `pitch` nodes per row: a pure
+ * HBM stream of 2 + 2 bytes per node, coalesced on both sides. */
+__global__ void __launch_bounds__(256) ingest_kernel(uint16_t * __restrict__ dst, int pitch,
+    const uint16_t * __restrict__ raw, int nx, int ny, int big_endian, int north_first)
+{
+        const size_t total = (size_t)nx * (size_t)ny;
+        const size_t stride = (size_t)gridDim.x * blockDim.x;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+                const int iy = (int)(i / (size_t)nx);
+                const int ix = (int)(i - (size_t)iy * nx);
+                uint16_t v = raw[i];
+                if (big_endian) v = (uint16_t)((v << 8) | (v >> 8));
+                const int oy = north_first ? ny - 1 - iy : iy;
+                dst[(size_t)oy * pitch + ix] = v;
+        }
+}
+
 /* ---- self test of tb::divide against the compiler's IEEE division ---------------- */
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x)
@@ -1037,7 +1149,10 @@ __global__ void __launch_bounds__(256) dfma_kernel(double * out, int iterations)
 
 namespace {
 const int N_SLOTS = 3;              /* host-pointer pipeline depth */
-const size_t CHUNK_RAYS = 1u << 20; /* rays per pipeline chunk */
+const size_t CHUNK_RAYS = 1u << 20; /* rays per pipeline chunk (one kernel per chunk) */
+const int STREAM_CHUNK_SHIFT = 19;  /* rays per copy of a streamed call: 512 Ki */
+const size_t STREAM_CHUNK_RAYS = (size_t)1 << STREAM_CHUNK_SHIFT;
+const int N_DRAINS = 4;             /* result streams of a streamed call */
 }
 
 struct turtle_plan {
@@ -1049,12 +1164,14 @@ struct turtle_plan {
         tb::MapDesc * d_maps;
         tb::TileRec * d_tiles;
         size_t bytes;
+        turtle_residency_report report;
         std::vector<struct turtle_stack *> pinned;
         unsigned long long * d_counters; /* N_SLOTS + 1 triplets */
         turtle_plan_counters counters;
         /* ray scheduling (turtle_plan_schedule_set) */
         int schedule;
         int specialise; /* turtle_plan_specialise_set */
+        int pipeline_mode; /* turtle_plan_pipeline_set */
         unsigned * d_sched[4]; /* per pipeline slot: keys, index, keys', order */
         void * d_sched_tmp[4];
         size_t sched_rays[4], sched_tmp_bytes[4];
@@ -1064,6 +1181,15 @@ struct turtle_plan {
         double * d_in[N_SLOTS];
         turtle_trace_result * d_out[N_SLOTS];
         size_t slot_rays;
+        /* streamed host-pointer calls (trace_streamed) */
+        double * d_all_in;
+        turtle_trace_result * d_all_out;
+        size_t all_rays;
+        unsigned long long * d_stream_state; /* watermark + per-chunk counters */
+        unsigned long long * h_marks;        /* pinned: the watermark values to copy */
+        size_t stream_chunks;
+        cudaEvent_t ev_reset;
+        cudaStream_t drain[4]; /* N_DRAINS result streams */
 };
 
 struct turtle_states {
@@ -1137,25 +1263,79 @@ static size_t padded_nodes(const struct turtle_map * map, int * pitch)
         return (size_t)*pitch * (size_t)(map->ny + 1);
 }
 
-extern "C" enum turtle_return turtle_stepper_freeze(
-    struct turtle_stepper * stepper, int device, struct turtle_plan ** plan_)
+static enum turtle_return check_rule(turtle_function_t * fn, const struct turtle_trace_rule * rule);
+
+static size_t padded_shape(int nx, int ny, int * pitch)
+{
+        *pitch = round_up(nx, 16);
+        return (size_t)*pitch * (size_t)(ny + 1);
+}
+
+static double wall_ms()
+{
+        struct timespec t;
+        clock_gettime(CLOCK_MONOTONIC, &t);
+        return 1e3 * (double)t.tv_sec + 1e-6 * (double)t.tv_nsec;
+}
+
+/* One tile that is not on the host: file -> nodes in file order -> device -> ingest_kernel. */
+static enum turtle_return ingest_tile(turtle_function_t * fn, const std::string & path,
+    const tb::MapDesc & want, uint16_t * dst, int pitch, uint16_t ** scratch,
+    size_t * scratch_nodes, turtle_residency_report * report)
+{
+        tbio::Header h;
+        tbio::RawLayout layout;
+        tbio::Error err;
+        std::vector<uint16_t> raw;
+        const double t0 = wall_ms();
+        if (tbio::read_map(path.c_str(), h, layout, raw, err) != 0)
+                return tbh::raise(fn, err.code, err.file, __LINE__, "%s", err.message.c_str());
+        if ((h.nx != want.nx) || (h.ny != want.ny))
+                return tbh::raise(fn, TURTLE_RETURN_BAD_FORMAT, BATCH_CU, __LINE__,
+                    "tile `%s' changed since the stack was created", path.c_str());
+        const double t1 = wall_ms();
+        if (*scratch_nodes < raw.size()) {
+                cudaFree(*scratch);
+                *scratch = NULL;
+                *scratch_nodes = 0;
+                CUDA_TRY(fn, cudaMalloc((void **)scratch, raw.size() * sizeof(uint16_t)));
+                *scratch_nodes = raw.size();
+        }
+        CUDA_TRY(fn, cudaMemcpy(*scratch, raw.data(), raw.size() * sizeof(uint16_t),
+                         cudaMemcpyHostToDevice));
+        const int blocks = (int)std::min<size_t>((raw.size() + 255) / 256, 148 * 16);
+        ingest_kernel<<<blocks, 256>>>(dst, pitch, *scratch, h.nx, h.ny, layout.big_endian,
+            layout.north_first);
+        CUDA_TRY(fn, cudaGetLastError());
+        CUDA_TRY(fn, cudaDeviceSynchronize()); /* the scratch buffer is reused */
+        report->read_ms += t1 - t0;
+        report->upload_ms += wall_ms() - t1;
+        report->tiles_ingested++;
+        return TURTLE_RETURN_SUCCESS;
+}
+
+static enum turtle_return freeze_plan(turtle_function_t * fn, struct turtle_stepper * stepper,
+    int device, const struct turtle_residency * region, struct turtle_plan ** plan_)
 {
         *plan_ = NULL;
-        enum turtle_return rc = require_device(FN(&turtle_stepper_freeze), device);
+        enum turtle_return rc = require_device(fn, device);
         if (rc != TURTLE_RETURN_SUCCESS) return rc;
         if (stepper->layers.empty() || stepper->layers[0].empty())
-                return tbh::raise(FN(&turtle_stepper_freeze), TURTLE_RETURN_DOMAIN_ERROR,
-                    BATCH_CU, __LINE__, "empty geometry");
-        rc = tbh::stepper_flatten(stepper, FN(&turtle_stepper_freeze));
+                return tbh::raise(fn, TURTLE_RETURN_DOMAIN_ERROR, BATCH_CU, __LINE__,
+                    "empty geometry");
+        /* a flattening of its own: tiles that are not on the host stay on disk until they
+         * are ingested below, and the region leaves tiles out */
+        tb_flat_geometry F;
+        rc = tbh::flatten_into(stepper, F, fn, 0, region);
         if (rc != TURTLE_RETURN_SUCCESS) return rc;
-        const tb_flat_geometry & F = stepper->flat;
 
-        CUDA_TRY(&turtle_stepper_freeze, cudaSetDevice(device));
+        CUDA_TRY(fn, cudaSetDevice(device));
         struct turtle_plan * plan = new (std::nothrow) turtle_plan();
         if (plan == NULL)
-                return tbh::raise(FN(&turtle_stepper_freeze), TURTLE_RETURN_MEMORY_ERROR,
-                    BATCH_CU, __LINE__, "could not allocate memory");
+                return tbh::raise(fn, TURTLE_RETURN_MEMORY_ERROR, BATCH_CU, __LINE__,
+                    "could not allocate memory");
         memset(&plan->counters, 0x0, sizeof(plan->counters));
+        memset(&plan->report, 0x0, sizeof(plan->report));
         plan->device = device;
         plan->pool = NULL;
         plan->d_maps = NULL;
@@ -1163,6 +1343,7 @@ extern "C" enum turtle_return turtle_stepper_freeze(
         plan->d_counters = NULL;
         plan->schedule = 0;
         plan->specialise = 1;
+        plan->pipeline_mode = 0;
         for (int s = 0; s < 4; s++) {
                 plan->d_sched[s] = NULL;
                 plan->d_sched_tmp[s] = NULL;
@@ -1175,6 +1356,14 @@ extern "C" enum turtle_return turtle_stepper_freeze(
                 plan->d_in[s] = NULL;
                 plan->d_out[s] = NULL;
         }
+        plan->d_all_in = NULL;
+        plan->d_all_out = NULL;
+        plan->all_rays = 0;
+        plan->d_stream_state = NULL;
+        plan->h_marks = NULL;
+        plan->stream_chunks = 0;
+        plan->ev_reset = NULL;
+        for (int j = 0; j < 4; j++) plan->drain[j] = NULL;
         cudaDeviceProp prop;
         cudaGetDeviceProperties(&prop, device);
         plan->sm_count = prop.multiProcessorCount;
@@ -1185,35 +1374,73 @@ extern "C" enum turtle_return turtle_stepper_freeze(
         const size_t n_maps = F.maps.size();
         std::vector<size_t> offset(n_maps, 0);
         std::vector<int> pitch(n_maps, 0);
+        std::vector<size_t> owner(n_maps, 0); /* first descriptor of the same grid */
         std::map<const struct turtle_map *, size_t> first;
         size_t total = 0;
         for (size_t i = 0; i < n_maps; i++) {
-                std::map<const struct turtle_map *, size_t>::iterator it = first.find(F.src[i]);
-                if (it != first.end()) {
-                        offset[i] = offset[it->second];
-                        pitch[i] = pitch[it->second];
-                        continue;
+                owner[i] = i;
+                if (F.src[i] != NULL) {
+                        std::map<const struct turtle_map *, size_t>::iterator it =
+                            first.find(F.src[i]);
+                        if (it != first.end()) {
+                                owner[i] = it->second;
+                                offset[i] = offset[it->second];
+                                pitch[i] = pitch[it->second];
+                                continue;
+                        }
+                        first[F.src[i]] = i;
                 }
-                first[F.src[i]] = i;
                 offset[i] = total;
-                total += (padded_nodes(F.src[i], &pitch[i]) + 127) / 128 * 128;
+                total += (padded_shape(F.maps[i].nx, F.maps[i].ny, &pitch[i]) + 127) / 128 * 128;
         }
         const size_t pool_bytes = std::max<size_t>(total, 128) * sizeof(uint16_t);
+        size_t limit = (region != NULL) ? region->memory_limit : 0;
+        if (limit == 0) {
+                size_t free_bytes = 0, total_bytes = 0;
+                if (cudaMemGetInfo(&free_bytes, &total_bytes) == cudaSuccess) limit = free_bytes;
+        }
+        if ((limit > 0) && (pool_bytes > limit)) {
+                delete plan;
+                return tbh::raise(fn, TURTLE_RETURN_MEMORY_ERROR, BATCH_CU, __LINE__,
+                    "the residency plan needs %zu bytes of device memory for %zu grids, "
+                    "%zu are allowed: restrict the region (turtle_stepper_freeze_region)",
+                    pool_bytes, n_maps, limit);
+        }
         cudaError_t err = cudaMalloc(&plan->pool, pool_bytes);
         if (err == cudaSuccess) err = cudaMemset(plan->pool, 0x0, pool_bytes);
         std::vector<tb::MapDesc> maps = F.maps;
+        uint16_t * scratch = NULL;
+        size_t scratch_nodes = 0;
         for (size_t i = 0; (i < n_maps) && (err == cudaSuccess); i++) {
                 uint16_t * dst = (uint16_t *)plan->pool + offset[i];
                 maps[i].nodes = dst;
                 maps[i].pitch = pitch[i];
-                if (first[F.src[i]] == i) err = upload_nodes(dst, pitch[i], F.src[i]);
+                if (owner[i] != i) continue;
+                if (F.src[i] != NULL) {
+                        const double t0 = wall_ms();
+                        err = upload_nodes(dst, pitch[i], F.src[i]);
+                        plan->report.upload_ms += wall_ms() - t0;
+                } else {
+                        rc = ingest_tile(fn, F.file[i], F.maps[i], dst, pitch[i], &scratch,
+                            &scratch_nodes, &plan->report);
+                        if (rc != TURTLE_RETURN_SUCCESS) {
+                                cudaFree(scratch);
+                                turtle_plan_destroy(&plan);
+                                return rc;
+                        }
+                }
         }
+        cudaFree(scratch);
         const size_t maps_bytes = std::max<size_t>(n_maps, 1) * sizeof(tb::MapDesc);
         const size_t tiles_bytes = std::max<size_t>(F.tiles.size(), 1) * sizeof(tb::TileRec);
         /* device copies of the tile records: device node pointers and padded pitch */
         std::vector<tb::TileRec> tiles = F.tiles;
         for (size_t i = 0; i < tiles.size(); i++)
-                if (tiles[i].map >= 0) tiles[i].nodes = maps[tiles[i].map].nodes;
+                if (tiles[i].map >= 0) {
+                        tiles[i].nodes = maps[tiles[i].map].nodes;
+                        plan->report.tiles_resident++;
+                }
+        plan->report.tiles_skipped = F.skipped;
         if (err == cudaSuccess) err = cudaMalloc((void **)&plan->d_maps, maps_bytes);
         if ((err == cudaSuccess) && n_maps)
                 err = cudaMemcpy(plan->d_maps, maps.data(), n_maps * sizeof(tb::MapDesc),
@@ -1227,9 +1454,8 @@ extern "C" enum turtle_return turtle_stepper_freeze(
                     (N_SLOTS + 1) * 4 * sizeof(unsigned long long));
         if (err != cudaSuccess) {
                 turtle_plan_destroy(&plan);
-                return tbh::raise(FN(&turtle_stepper_freeze), TURTLE_RETURN_LIBRARY_ERROR,
-                    BATCH_CU, __LINE__, "CUDA error while uploading the geometry: %s",
-                    cudaGetErrorString(err));
+                return tbh::raise(fn, TURTLE_RETURN_LIBRARY_ERROR, BATCH_CU, __LINE__,
+                    "CUDA error while uploading the geometry: %s", cudaGetErrorString(err));
         }
         plan->G = F.G;
         plan->G.maps = plan->d_maps;
@@ -1245,7 +1471,81 @@ extern "C" enum turtle_return turtle_stepper_freeze(
                 }
         }
         plan->bytes = pool_bytes + maps_bytes + tiles_bytes;
+        plan->report.bytes = plan->bytes;
         *plan_ = plan;
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_stepper_freeze(
+    struct turtle_stepper * stepper, int device, struct turtle_plan ** plan_)
+{
+        return freeze_plan(FN(&turtle_stepper_freeze), stepper, device, NULL, plan_);
+}
+
+extern "C" enum turtle_return turtle_stepper_freeze_region(struct turtle_stepper * stepper,
+    int device, const struct turtle_residency * region, struct turtle_plan ** plan_)
+{
+        return freeze_plan(FN(&turtle_stepper_freeze_region), stepper, device, region, plan_);
+}
+
+extern "C" void turtle_plan_residency_get(
+    const struct turtle_plan * plan, struct turtle_residency_report * report)
+{
+        *report = plan->report;
+}
+
+/* Bounding box of the ground tracks of the rays (turtle_b200.h). Host code: it runs
+ * once per batch, before the plan exists. */
+extern "C" enum turtle_return turtle_residency_from_rays(size_t n, const double * position,
+    const double * direction, const struct turtle_trace_rule * rule, double step,
+    double margin, struct turtle_residency * region)
+{
+        enum turtle_return rc = check_rule(FN(&turtle_residency_from_rays), rule);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        if (!(step > 0.)) step = 1000.;
+        double la0 = DBL_MAX, la1 = -DBL_MAX, lo0 = DBL_MAX, lo1 = -DBL_MAX;
+        bool open_longitude = false;
+        const double radius = TB_WGS84_A + rule->altitude_max;
+        for (size_t i = 0; i < n; i++) {
+                const double * p = position + 3 * i;
+                const double * d = direction + 3 * i;
+                const double dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+                if (!(dd > 0.) || !isfinite(dd) || !isfinite(p[0] + p[1] + p[2])) continue;
+                /* path length at which the ray is above altitude_max for certain: the
+                 * geocentric radius of a point at altitude h is at most a + h */
+                const double pd = p[0] * d[0] + p[1] * d[1] + p[2] * d[2];
+                const double pp = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+                const double disc = pd * pd - dd * (pp - radius * radius);
+                double reach = (disc > 0.) ? (-pd + sqrt(disc)) / dd * sqrt(dd) : 0.;
+                if (!(reach > 0.)) reach = 0.;
+                if (reach > rule->length_max) reach = rule->length_max;
+                const double norm = sqrt(dd);
+                const int pieces = (int)std::min(1e6, ceil(reach / step)) + 1;
+                double previous = 0.;
+                for (int k = 0; k <= pieces; k++) {
+                        const double t = reach * k / pieces / norm;
+                        const double q[3] = { p[0] + d[0] * t, p[1] + d[1] * t, p[2] + d[2] * t };
+                        double la, lo, al;
+                        tb::ecef_to_geodetic(q, la, lo, al);
+                        if ((q[0] == 0.) && (q[1] == 0.)) open_longitude = true;
+                        if ((k > 0) && (fabs(lo - previous) > 180.)) open_longitude = true;
+                        previous = lo;
+                        la0 = std::min(la0, la);
+                        la1 = std::max(la1, la);
+                        lo0 = std::min(lo0, lo);
+                        lo1 = std::max(lo1, lo);
+                }
+        }
+        region->memory_limit = 0;
+        if (la0 > la1) { /* no valid ray: an empty box */
+                region->latitude_min = region->longitude_min = DBL_MAX;
+                region->latitude_max = region->longitude_max = -DBL_MAX;
+                return TURTLE_RETURN_SUCCESS;
+        }
+        region->latitude_min = la0 - margin;
+        region->latitude_max = la1 + margin;
+        region->longitude_min = open_longitude ? NAN : lo0 - margin;
+        region->longitude_max = open_longitude ? NAN : lo1 + margin;
         return TURTLE_RETURN_SUCCESS;
 }
 
@@ -1268,6 +1568,13 @@ extern "C" void turtle_plan_destroy(struct turtle_plan ** plan_)
                 cudaFree(plan->d_sched[s]);
                 cudaFree(plan->d_sched_tmp[s]);
         }
+        cudaFree(plan->d_all_in);
+        cudaFree(plan->d_all_out);
+        cudaFree(plan->d_stream_state);
+        if (plan->h_marks != NULL) cudaFreeHost(plan->h_marks);
+        if (plan->ev_reset != NULL) cudaEventDestroy(plan->ev_reset);
+        for (int j = 0; j < 4; j++)
+                if (plan->drain[j] != NULL) cudaStreamDestroy(plan->drain[j]);
         cudaFree(plan->pool);
         cudaFree(plan->d_maps);
         cudaFree(plan->d_tiles);
@@ -1299,6 +1606,11 @@ extern "C" void turtle_plan_schedule_set(struct turtle_plan * plan, int mode)
 extern "C" void turtle_plan_specialise_set(struct turtle_plan * plan, int enable)
 {
         plan->specialise = enable;
+}
+
+extern "C" void turtle_plan_pipeline_set(struct turtle_plan * plan, int mode)
+{
+        plan->pipeline_mode = mode;
 }
 
 /* Build the queue order of a launch (longest-expected-first) in plan->d_sched. */
@@ -1368,11 +1680,12 @@ static enum turtle_return check_rule(turtle_function_t * fn, const struct turtle
 /* Launch one instance of the trace kernel. The shared-memory carve-out is asked to be
  * just what the resident CTAs need: whatever they leave of the 256 kB is L1 for the DEM
  * gathers (the default heuristic takes the next larger configuration). */
-template <bool LLA, bool PROJ, int MINB, int SHAPE>
+template <bool LLA, bool PROJ, int MINB, int SHAPE, bool STREAM = false>
 static void trace_start(const struct turtle_plan * plan, int per_sm, int blocks, int threads,
     cudaStream_t stream, const TraceArgs & A)
 {
-        void (*kernel)(const tb::Geometry, const TraceArgs) = trace_kernel<LLA, PROJ, MINB, SHAPE>;
+        void (*kernel)(const tb::Geometry, const TraceArgs) =
+            trace_kernel<LLA, PROJ, MINB, SHAPE, STREAM>;
         static int carveout_of[16] = { 0 };
         const int key = per_sm & 15;
         if (carveout_of[key] == 0) {
@@ -1392,16 +1705,28 @@ static void trace_start(const struct turtle_plan * plan, int per_sm, int blocks,
         kernel<<<blocks, threads, 0, stream>>>(plan->G, A);
 }
 
+/* Device state of a streamed call: [0] watermark, then one counter per chunk. */
+struct StreamState {
+        int chunk_shift;
+        const unsigned long long * watermark;
+        unsigned * chunk_done;
+};
+
 static cudaError_t launch_trace(struct turtle_plan * plan, int slot, size_t n,
     const double * d_position, const double * d_direction,
     const struct turtle_trace_rule * rule, struct turtle_trace_result * d_results,
-    unsigned long long * d_counters, cudaStream_t stream)
+    unsigned long long * d_counters, cudaStream_t stream, const StreamState * streamed = NULL)
 {
         cudaError_t err = cudaMemsetAsync(d_counters, 0x0, 4 * sizeof(unsigned long long), stream);
         if (err != cudaSuccess) return err;
         TraceArgs A;
         A.n = n;
-        err = schedule_rays(plan, slot, n, d_position, d_direction, stream, &A.order);
+        A.chunk_shift = (streamed != NULL) ? streamed->chunk_shift : 0;
+        A.watermark = (streamed != NULL) ? streamed->watermark : NULL;
+        A.chunk_done = (streamed != NULL) ? streamed->chunk_done : NULL;
+        A.order = NULL;
+        if (streamed == NULL)
+                err = schedule_rays(plan, slot, n, d_position, d_direction, stream, &A.order);
         if (err != cudaSuccess) return err;
         A.position = d_position;
         A.direction = d_direction;
@@ -1430,11 +1755,25 @@ static cudaError_t launch_trace(struct turtle_plan * plan, int slot, size_t n,
         } while (0)
         /* the register budget follows the requested residency (in units of 128 threads) */
         const int minb = per_sm * threads / 128;
-        if (plan->specialise && (tb::geometry_shape(plan->G) == tb::SHAPE_STACK)) {
+        const bool stack_shape = plan->specialise && (tb::geometry_shape(plan->G) == tb::SHAPE_STACK);
+        if (streamed != NULL) {
+                /* streamed calls: the kernels waiting for their rays, 6 CTAs per SM */
+                const int cap = plan->sm_count * 6;
+                if (blocks > cap) blocks = cap;
+                const int sm6 = (per_sm < 6) ? per_sm : 6;
+                if (stack_shape)
+                        trace_start<false, false, 6, tb::SHAPE_STACK, true>(plan, sm6, blocks, threads, stream, A);
+                else if (lla && proj)
+                        trace_start<true, true, 6, tb::SHAPE_GENERIC, true>(plan, sm6, blocks, threads, stream, A);
+                else if (lla)
+                        trace_start<true, false, 6, tb::SHAPE_GENERIC, true>(plan, sm6, blocks, threads, stream, A);
+                else if (proj)
+                        trace_start<false, true, 6, tb::SHAPE_GENERIC, true>(plan, sm6, blocks, threads, stream, A);
+                else
+                        trace_start<false, false, 6, tb::SHAPE_GENERIC, true>(plan, sm6, blocks, threads, stream, A);
+        } else if (stack_shape) {
                 if (minb <= 6)
                         trace_start<false, false, 6, tb::SHAPE_STACK>(plan, per_sm, blocks, threads, stream, A);
-                else if (minb == 7)
-                        trace_start<false, false, 7, tb::SHAPE_STACK>(plan, per_sm, blocks, threads, stream, A);
                 else
                         trace_start<false, false, 8, tb::SHAPE_STACK>(plan, per_sm, blocks, threads, stream, A);
         } else if (minb <= 4)
@@ -1509,6 +1848,128 @@ extern "C" void turtle_plan_counters_sync(struct turtle_plan * plan)
         }
 }
 
+/* Host-pointer call, streamed: ONE persistent trace kernel over all the rays while the
+ * copy engines feed and drain it.
+ *   stream 1 (H2D): for each chunk, positions and directions, then the new watermark
+ *                   (an 8-byte copy, ordered after the data of the chunk);
+ *   stream 0      : the trace kernel -- a lane that holds ticket q waits until the
+ *                   watermark has passed q (MODE_WAIT), and every finished ray is counted
+ *                   for its chunk after a __threadfence;
+ *   stream 2 (D2H): for each chunk, a one-thread kernel that waits for the chunk's count,
+ *                   then the copy of its records.
+ * Compared with one kernel per chunk there is a single kernel tail instead of one per
+ * chunk, and no lane ever idles between chunks. */
+static enum turtle_return trace_streamed(struct turtle_plan * plan, size_t n,
+    const double * position, const double * direction, const struct turtle_trace_rule * rule,
+    struct turtle_trace_result * results, int chunk_shift)
+{
+        turtle_function_t * fn = FN(&turtle_stepper_trace_batch);
+        const size_t chunk = (size_t)1 << chunk_shift;
+        const size_t n_chunks = (n + chunk - 1) / chunk;
+        CUDA_TRY(fn, plan_pipeline(plan, 1)); /* the three streams and their events */
+        if (plan->ev_reset == NULL) CUDA_TRY(fn, cudaEventCreate(&plan->ev_reset));
+        if (plan->all_rays < n) {
+                cudaFree(plan->d_all_in);
+                cudaFree(plan->d_all_out);
+                plan->d_all_in = NULL;
+                plan->d_all_out = NULL;
+                plan->all_rays = 0;
+                CUDA_TRY(fn, cudaMalloc((void **)&plan->d_all_in, (n * 6 + 32) * sizeof(double)));
+                CUDA_TRY(fn, cudaMalloc((void **)&plan->d_all_out, n * sizeof(turtle_trace_result)));
+                plan->all_rays = n;
+        }
+        if (plan->stream_chunks < n_chunks) {
+                cudaFree(plan->d_stream_state);
+                if (plan->h_marks != NULL) cudaFreeHost(plan->h_marks);
+                plan->d_stream_state = NULL;
+                plan->h_marks = NULL;
+                plan->stream_chunks = 0;
+                CUDA_TRY(fn, cudaMalloc((void **)&plan->d_stream_state,
+                                 (n_chunks + 2) * sizeof(unsigned long long)));
+                CUDA_TRY(fn, cudaHostAlloc((void **)&plan->h_marks,
+                                 (n_chunks + 1) * sizeof(unsigned long long), cudaHostAllocDefault));
+                plan->stream_chunks = n_chunks;
+        }
+        cudaStream_t compute = plan->stream[0], h2d = plan->stream[1];
+        for (int j = 0; j < N_DRAINS; j++)
+                if (plan->drain[j] == NULL)
+                        CUDA_TRY(fn, cudaStreamCreateWithFlags(&plan->drain[j], cudaStreamNonBlocking));
+        unsigned long long * d_counters = plan->d_counters + 4 * 0;
+        /* both arrays start on a 256-byte boundary and a chunk is a multiple of 128 bytes:
+         * no cache line holds rays of two chunks */
+        double * d_pos = plan->d_all_in;
+        double * d_dir = plan->d_all_in + (3 * n + 31) / 32 * 32;
+        StreamState st;
+        st.chunk_shift = chunk_shift;
+        st.watermark = plan->d_stream_state;
+        st.chunk_done = (unsigned *)(plan->d_stream_state + 1);
+
+        /* reset the stream state, then start the kernel: it waits for its rays */
+        CUDA_TRY(fn, cudaMemsetAsync(plan->d_stream_state, 0x0,
+                         (n_chunks + 2) * sizeof(unsigned long long), compute));
+        CUDA_TRY(fn, cudaEventRecord(plan->ev_reset, compute));
+        CUDA_TRY(fn, cudaStreamWaitEvent(h2d, plan->ev_reset, 0));
+        for (int j = 0; j < N_DRAINS; j++)
+                CUDA_TRY(fn, cudaStreamWaitEvent(plan->drain[j], plan->ev_reset, 0));
+        CUDA_TRY(fn, cudaEventRecord(plan->ev0[0], compute));
+        CUDA_TRY(fn, launch_trace(plan, 0, n, d_pos, d_dir, rule, plan->d_all_out, d_counters,
+                         compute, &st));
+        CUDA_TRY(fn, cudaEventRecord(plan->ev1[0], compute));
+        plan->counters.launches = 0;
+
+        /* from here on a failure must release the kernel before it is reported */
+        cudaError_t err = cudaSuccess;
+        for (size_t k = 0; (k < n_chunks) && (err == cudaSuccess); k++) {
+                const size_t i0 = k * chunk;
+                const size_t m = std::min(chunk, n - i0);
+                plan->h_marks[k] = i0 + m;
+                err = cudaMemcpyAsync(d_pos + 3 * i0, position + 3 * i0, m * 3 * sizeof(double),
+                    cudaMemcpyHostToDevice, h2d);
+                if (err == cudaSuccess)
+                        err = cudaMemcpyAsync(d_dir + 3 * i0, direction + 3 * i0,
+                            m * 3 * sizeof(double), cudaMemcpyHostToDevice, h2d);
+                if (err == cudaSuccess)
+                        err = cudaMemcpyAsync(plan->d_stream_state, &plan->h_marks[k],
+                            sizeof(unsigned long long), cudaMemcpyHostToDevice, h2d);
+        }
+        /* chunks do not complete in order (a chunk waits for its longest ray): the drains
+         * are dealt round robin to N_DRAINS streams, so that a late chunk only holds back
+         * the chunks queued behind it on its own stream */
+        for (size_t k = 0; (k < n_chunks) && (err == cudaSuccess); k++) {
+                const size_t i0 = k * chunk;
+                const size_t m = std::min(chunk, n - i0);
+                cudaStream_t out = plan->drain[k % N_DRAINS];
+                wait_chunk_kernel<<<1, 1, 0, out>>>(st.chunk_done + k, (unsigned)m, st.watermark);
+                plan->counters.launches++;
+                err = cudaGetLastError();
+                if (err == cudaSuccess)
+                        err = cudaMemcpyAsync(results + i0, plan->d_all_out + i0,
+                            m * sizeof(turtle_trace_result), cudaMemcpyDeviceToHost, out);
+        }
+        if (err != cudaSuccess) { /* wake every waiter up, drain, then report */
+                plan->h_marks[n_chunks] = STREAM_ABORT;
+                cudaStreamSynchronize(h2d);
+                cudaMemcpyAsync(plan->d_stream_state, &plan->h_marks[n_chunks],
+                    sizeof(unsigned long long), cudaMemcpyHostToDevice, h2d);
+                cudaDeviceSynchronize();
+                return tbh::raise(fn, TURTLE_RETURN_LIBRARY_ERROR, BATCH_CU, __LINE__,
+                    "CUDA error in the streamed trace: %s", cudaGetErrorString(err));
+        }
+        CUDA_TRY(fn, cudaStreamSynchronize(h2d));
+        CUDA_TRY(fn, cudaStreamSynchronize(compute));
+        for (int j = 0; j < N_DRAINS; j++) CUDA_TRY(fn, cudaStreamSynchronize(plan->drain[j]));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, plan->ev0[0], plan->ev1[0]);
+        unsigned long long c4[4];
+        CUDA_TRY(fn, cudaMemcpy(c4, d_counters, sizeof c4, cudaMemcpyDeviceToHost));
+        plan->counters.rays = n;
+        plan->counters.steps = c4[1];
+        plan->counters.samples = c4[2];
+        plan->counters.kernel_ms = ms;
+        plan->counters.launches += 1;
+        return TURTLE_RETURN_SUCCESS;
+}
+
 extern "C" enum turtle_return turtle_stepper_trace_batch(
     struct turtle_plan * plan, size_t n, const double * position,
     const double * direction, const struct turtle_trace_rule * rule,
@@ -1519,7 +1980,16 @@ extern "C" enum turtle_return turtle_stepper_trace_batch(
         memset(&plan->counters, 0x0, sizeof(plan->counters));
         if (n == 0) return TURTLE_RETURN_SUCCESS;
         CUDA_TRY(&turtle_stepper_trace_batch, cudaSetDevice(plan->device));
-        const size_t chunk = std::min(n, CHUNK_RAYS);
+        /* more than one chunk, caller's ray order: stream the batch through one kernel */
+        if ((plan->schedule == 0) && (plan->pipeline_mode != 1) && (n > STREAM_CHUNK_RAYS))
+                return trace_streamed(plan, n, position, direction, rule, results,
+                    STREAM_CHUNK_SHIFT);
+        size_t chunk_rays = CHUNK_RAYS;
+        if (getenv("TURTLE_B200_CHUNK_RAYS") != NULL) { /* development: pipeline sweep */
+                const long long v = atoll(getenv("TURTLE_B200_CHUNK_RAYS"));
+                if (v >= 1024) chunk_rays = (size_t)v;
+        }
+        const size_t chunk = std::min(n, chunk_rays);
         CUDA_TRY(&turtle_stepper_trace_batch, plan_pipeline(plan, chunk));
 
         /* chunked 3-deep pipeline: H2D(c+1) | kernel(c) | D2H(c-1) on 3 streams */
