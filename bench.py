@@ -44,17 +44,22 @@ DET_LAT, DET_LON, DET_HEIGHT = 46.5, 3.5, 1.0
 STACK_LAT0, STACK_LON0, STACK_N = 45, 2, 3
 ALTITUDE_MAX, MAX_STEPS = 9000.0, 100000
 N_AZ = N_EL = 4096
-# ALGORITHMIC FP64-pipe instructions (DFMA/DMUL/DADD/DSETP, FMA = 1) per geodetic-stack
-# sample = 382: the dynamic count of the straightforward expansion of the reference's
-# expressions (IEEE divisions, sqrt, library asin/atan2), measured with ncu on the first
-# kernel of this round (profiles/r01_trace_kernel_ncu_full.md). SURVEY.md App. C's static
-# estimate is 480 (it counts both asin/acos branches). The current kernel EXECUTES 264 per
-# sample (shared reciprocals, own asin/atan2: profiles/r01c_trace_kernel_ncu_full.md), so
-# its measured FP64-pipe utilisation (ncu: 47 %) is lower than the algorithmic fraction.
-OPS_PER_SAMPLE = 382.0
-EXECUTED_OPS_PER_SAMPLE = 264.0
+# FP64-pipe work per geodetic-stack sample (DFMA / DMUL / DADD / DSETP, one FMA = 1), in
+# lane slots of the pipe -- a warp instruction occupies 32 of them whatever its active mask:
+#   OPS_PER_SAMPLE      what the CURRENT kernel executes, from the committed ncu capture
+#                       (profiles/r01g_trace_kernel_ncu_full.md: FP64-pipe warp instructions
+#                       x 32 / samples). This is the roofline numerator: the smallest
+#                       instruction count known to compute the reference's expressions bit
+#                       for bit (exact divisions sharing reciprocals, own asin / atan2).
+#   NAIVE_OPS_PER_SAMPLE the straightforward expansion (IEEE divisions, library sqrt / asin /
+#                       atan2) measured on the first kernel of this round
+#                       (profiles/r01_trace_kernel_ncu_full.md); reported for reference only.
+OPS_PER_SAMPLE = 270.0
+NAIVE_OPS_PER_SAMPLE = 382.0
 BYTES_PER_RAY = 48 + 96  # position + direction in, result record out
 BYTES_PER_SAMPLE = 8     # four 16-bit nodes
+# DRAM traffic of one 16 Mi-ray launch (ncu --set full, profiles/r01g_trace_kernel_ncu_full.md)
+DRAM_BYTES_PER_LAUNCH = 7.9e9
 
 
 def stack_dir():
@@ -367,8 +372,9 @@ def main():
         e2e = {"value": world * n * args.steps / float(w.item()) / 1e6, "unit": "Mrays/s",
                "h2d_bytes_per_step": int(n * 48), "d2h_bytes_per_step": int(n * 96),
                "ms_per_step": 1e3 * float(w.item()) / args.steps,
-               "kernel_ms_sum_per_step": hc["kernel_ms"], "chunks_per_step": hc["launches"],
-               "api": "turtle_stepper_trace_batch (pinned host buffers, 3-deep chunk pipeline)"}
+               "kernel_ms_per_step": hc["kernel_ms"], "launches_per_step": hc["launches"],
+               "api": "turtle_stepper_trace_batch (pinned host buffers; one persistent kernel "
+                      "streamed by the copy engines in 256 Ki-ray pieces)"}
         # the two paths must agree bit for bit
         same = bool((torch.from_numpy(h_res.numpy()) == d_res.cpu()).all())
         e2e["matches_device_path"] = same
@@ -391,16 +397,17 @@ def main():
     achieved_ops = OPS_PER_SAMPLE * samples / (kernel_ms * 1e-3) / 1e12
     alg_bytes = n * BYTES_PER_RAY + samples * BYTES_PER_SAMPLE
     roofline = {
-        "kernel": "trace_kernel<false>", "bound": "fp64",
+        "kernel": "trace_kernel<LLA=0, PROJ=0, MINB=6, SHAPE_STACK>", "bound": "fp64",
         "achieved": achieved_ops, "peak": dfma / 1e3, "unit": "Tinst/s (FP64 pipe; FMA = 1)",
         "frac": achieved_ops / (dfma / 1e3) if dfma > 0 else None,
         "peak_source": "turtle_b200_dfma_peak() measured in this run (MEASURED_PEAKS.json has "
-                       "no FP64 entry)",
+                       "no FP64 entry; nominal 148 SM x 64 / clk x 1.965 GHz = 18.6)",
         "ops_per_sample": OPS_PER_SAMPLE, "samples_per_launch": samples,
-        "executed_ops_per_sample": EXECUTED_OPS_PER_SAMPLE,
-        "fp64_pipe_utilisation": EXECUTED_OPS_PER_SAMPLE * samples / (kernel_ms * 1e-3) / 1e12 /
-        (dfma / 1e3) if dfma > 0 else None,
-        "kernel_ms": kernel_ms, "traffic": None,
+        "ops_source": "executed by this kernel (ncu, profiles/r01g_trace_kernel_ncu_full.md)",
+        "naive_ops_per_sample": NAIVE_OPS_PER_SAMPLE,
+        "kernel_ms": kernel_ms, "traffic": DRAM_BYTES_PER_LAUNCH,
+        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu "
+                          "--set full (profiles/r01g_trace_kernel_ncu_full.md)",
         "hbm": {"achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak,
                 "unit": "GB/s", "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
                 "algorithmic_bytes": alg_bytes, "peak_source": hbm_src},

@@ -161,7 +161,7 @@ TURTLE_API void turtle_plan_schedule_set(struct turtle_plan * plan, int mode);
 TURTLE_API void turtle_plan_specialise_set(struct turtle_plan * plan, int enable);
 /* How the host-pointer call turtle_stepper_trace_batch overlaps its copies with the
  * stepping. 0 (default): streamed -- one persistent kernel over the whole batch, fed and
- * drained by the copy engines in 512 Ki-ray pieces (lanes wait for their ray, finished
+ * drained by the copy engines in 256 Ki-ray pieces (lanes wait for their ray, finished
  * chunks are copied back as they complete). 1: chunked -- one kernel per 1 Mi-ray chunk on
  * three streams (also used whenever a ray schedule is set). Results are identical. */
 TURTLE_API void turtle_plan_pipeline_set(struct turtle_plan * plan, int mode);

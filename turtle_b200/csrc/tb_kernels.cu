@@ -79,30 +79,37 @@ struct TraceArgs {
 };
 
 #define STREAM_ABORT (~0ull)
+#define STREAM_TIMEOUT_NS 20000000000ull /* a lane never waits longer for its ray */
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        return t;
+}
 
 /* A ray's record is complete: it must be visible before it is counted for its chunk.
  * The fence that guarantees it stalls the whole warp, so the count is deferred: the lane
- * remembers the chunk (`owed`) and the warp settles its debts every 32 iterations with
- * ONE fence (and when it exits). A lane that still owes a count when it finishes another
- * ray settles at once. */
+ * remembers what it owes (chunk in the high bits, number of rays in the low 8) and the
+ * warp settles its debts every 128 iterations with ONE fence (and when it runs dry). A
+ * lane that owes counts to another chunk when it finishes a ray settles at once. */
 __device__ __forceinline__ void record_done(const TraceArgs & A, unsigned long long ray,
     int & owed)
 {
-        if (A.chunk_done != NULL) {
-                if (owed >= 0) {
-                        __threadfence();
-                        atomicAdd(A.chunk_done + owed, 1u);
-                }
-                owed = (int)(ray >> A.chunk_shift);
+        const int chunk = (int)(ray >> A.chunk_shift);
+        if ((owed >= 0) && (((owed >> 8) != chunk) || ((owed & 0xff) == 0xff))) {
+                __threadfence();
+                atomicAdd(A.chunk_done + (owed >> 8), (unsigned)(owed & 0xff));
+                owed = -1;
         }
+        owed = (owed >= 0) ? owed + 1 : ((chunk << 8) | 1);
 }
 
 __device__ __forceinline__ void settle_done(const TraceArgs & A, int & owed)
 {
-        if (A.chunk_done == NULL) return;
         if (__any_sync(0xffffffffu, owed >= 0)) {
                 __threadfence();
-                if (owed >= 0) atomicAdd(A.chunk_done + owed, 1u);
+                if (owed >= 0) atomicAdd(A.chunk_done + (owed >> 8), (unsigned)(owed & 0xff));
                 owed = -1;
         }
 }
@@ -114,7 +121,11 @@ __global__ void wait_chunk_kernel(const unsigned * done, unsigned count,
 {
         const volatile unsigned * d = done;
         const volatile unsigned long long * w = watermark;
-        while ((*d < count) && (*w != STREAM_ABORT)) __nanosleep(2000);
+        const unsigned long long t0 = global_ns();
+        while ((*d < count) && (*w != STREAM_ABORT)) {
+                __nanosleep(2000);
+                if (global_ns() - t0 > 2ull * STREAM_TIMEOUT_NS) break; /* reported by the host */
+        }
 }
 
 __device__ __forceinline__ bool finite3(const double v[3])
@@ -170,9 +181,10 @@ __global__ void __launch_bounds__(128, MINB)
         bool pending_wait = false; /* warp uniform: some lane holds a ticket */
         int owed = -1;             /* chunk whose completion count this lane still owes */
         unsigned iteration = 0u;
+        const unsigned long long t_start = STREAM ? global_ns() : 0ull;
 
         for (;;) {
-                if (STREAM && ((++iteration & 31u) == 0u)) settle_done(A, owed);
+                if (STREAM && ((++iteration & 127u) == 0u)) settle_done(A, owed);
                 /* ---- refill idle lanes from the global ray queue ----------
                  * An idle lane takes a ticket q (one atomicAdd per warp, ballot / popc
                  * ranks) and WAITs until ray q is on the device: at once when the whole
@@ -206,7 +218,15 @@ __global__ void __launch_bounds__(128, MINB)
                                         const unsigned long long w =
                                             *(const volatile unsigned long long *)A.watermark;
                                         arrived = q < w;
-                                        if (w == STREAM_ABORT) mode = MODE_IDLE; /* host gave up */
+                                        if (w == STREAM_ABORT) {
+                                                mode = MODE_IDLE; /* the host gave up */
+                                        } else if (!arrived &&
+                                            (global_ns() - t_start > STREAM_TIMEOUT_NS)) {
+                                                /* the copies never came (a fault on the host
+                                                 * side): give the GPU back and flag it */
+                                                A.cursor[3] = 1ull;
+                                                mode = MODE_IDLE;
+                                        }
                                 }
                                 if (arrived && (mode == MODE_WAIT)) {
                                         const unsigned long long r =
@@ -1150,7 +1170,7 @@ __global__ void __launch_bounds__(256) dfma_kernel(double * out, int iterations)
 namespace {
 const int N_SLOTS = 3;              /* host-pointer pipeline depth */
 const size_t CHUNK_RAYS = 1u << 20; /* rays per pipeline chunk (one kernel per chunk) */
-const int STREAM_CHUNK_SHIFT = 19;  /* rays per copy of a streamed call: 512 Ki */
+const int STREAM_CHUNK_SHIFT = 18;  /* rays per copy of a streamed call: 256 Ki */
 const size_t STREAM_CHUNK_RAYS = (size_t)1 << STREAM_CHUNK_SHIFT;
 const int N_DRAINS = 4;             /* result streams of a streamed call */
 }
@@ -1904,20 +1924,16 @@ static enum turtle_return trace_streamed(struct turtle_plan * plan, size_t n,
         st.watermark = plan->d_stream_state;
         st.chunk_done = (unsigned *)(plan->d_stream_state + 1);
 
-        /* reset the stream state, then start the kernel: it waits for its rays */
+        /* reset the stream state; queue the copies in; THEN start the kernel, which waits
+         * for its rays. (This order also holds when kernel launches are made synchronous --
+         * a profiler, CUDA_LAUNCH_BLOCKING --: the copies are already on their way.) */
         CUDA_TRY(fn, cudaMemsetAsync(plan->d_stream_state, 0x0,
                          (n_chunks + 2) * sizeof(unsigned long long), compute));
         CUDA_TRY(fn, cudaEventRecord(plan->ev_reset, compute));
         CUDA_TRY(fn, cudaStreamWaitEvent(h2d, plan->ev_reset, 0));
         for (int j = 0; j < N_DRAINS; j++)
                 CUDA_TRY(fn, cudaStreamWaitEvent(plan->drain[j], plan->ev_reset, 0));
-        CUDA_TRY(fn, cudaEventRecord(plan->ev0[0], compute));
-        CUDA_TRY(fn, launch_trace(plan, 0, n, d_pos, d_dir, rule, plan->d_all_out, d_counters,
-                         compute, &st));
-        CUDA_TRY(fn, cudaEventRecord(plan->ev1[0], compute));
         plan->counters.launches = 0;
-
-        /* from here on a failure must release the kernel before it is reported */
         cudaError_t err = cudaSuccess;
         for (size_t k = 0; (k < n_chunks) && (err == cudaSuccess); k++) {
                 const size_t i0 = k * chunk;
@@ -1932,6 +1948,16 @@ static enum turtle_return trace_streamed(struct turtle_plan * plan, size_t n,
                         err = cudaMemcpyAsync(plan->d_stream_state, &plan->h_marks[k],
                             sizeof(unsigned long long), cudaMemcpyHostToDevice, h2d);
         }
+        if (err != cudaSuccess) { /* nothing waits yet */
+                cudaDeviceSynchronize();
+                return tbh::raise(fn, TURTLE_RETURN_LIBRARY_ERROR, BATCH_CU, __LINE__,
+                    "CUDA error in the streamed trace: %s", cudaGetErrorString(err));
+        }
+        CUDA_TRY(fn, cudaEventRecord(plan->ev0[0], compute));
+        err = launch_trace(plan, 0, n, d_pos, d_dir, rule, plan->d_all_out, d_counters, compute,
+            &st);
+        if (err == cudaSuccess) err = cudaEventRecord(plan->ev1[0], compute);
+        /* from here on a failure must release the waiters before it is reported */
         /* chunks do not complete in order (a chunk waits for its longest ray): the drains
          * are dealt round robin to N_DRAINS streams, so that a late chunk only holds back
          * the chunks queued behind it on its own stream */
@@ -1967,6 +1993,9 @@ static enum turtle_return trace_streamed(struct turtle_plan * plan, size_t n,
         plan->counters.samples = c4[2];
         plan->counters.kernel_ms = ms;
         plan->counters.launches += 1;
+        if (c4[3] != 0ull)
+                return tbh::raise(fn, TURTLE_RETURN_LIBRARY_ERROR, BATCH_CU, __LINE__,
+                    "the streamed trace timed out waiting for its rays to reach the device");
         return TURTLE_RETURN_SUCCESS;
 }
 
