@@ -11,8 +11,9 @@ leaves the stack (index[0] < 0), rises above 9000 m or after 1e5 steps.
 One "step" of this bench = one pass of the hot path over the whole batch of rays of
 every rank. Scaling is weak: each rank (one per GPU, DEM replicated) traces its own
 16 Mi rays -- with N ranks the fan has N x 4096 azimuths and rank r takes azimuths
-r, r + N, ... --; rank 0 then gathers the 96-byte result records of all ranks over
-NCCL, inside the timed region.
+r, r + N, ... --; the 96-byte result records of all ranks land in rank 0's memory inside the
+timed region: each rank's trace kernel stores them there itself over NVLink (CUDA IPC peer
+mapping, turtle_b200.dist.PeerRecords), with an NCCL gather as the fall-back.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--rays R] [--impl reference]
 
