@@ -59,7 +59,8 @@ namespace {
 
 enum { MODE_IDLE = 0, MODE_INIT = 1, MODE_TENT = 2, MODE_BISECT = 3, MODE_REBUILD = 4,
        MODE_FINISH = 5,
-       MODE_WAIT = 6 /* holds a queue ticket whose ray has not arrived on the device yet */ };
+       MODE_WAIT = 6, /* holds a queue ticket whose ray has not arrived on the device yet */
+       MODE_DONE = 7  /* trace: the record is complete in shared memory, to be written out */ };
 
 struct TraceArgs {
         unsigned long long n;
@@ -88,27 +89,18 @@ __device__ __forceinline__ unsigned long long global_ns()
         return t;
 }
 
-/* A ray's record is complete: it must be visible before it is counted for its chunk.
- * The fence that guarantees it stalls the whole warp, so the count is deferred: the lane
- * remembers what it owes (chunk in the high bits, number of rays in the low 8) and the
- * warp settles its debts every 128 iterations with ONE fence (and when it runs dry). A
- * lane that owes counts to another chunk when it finishes a ray settles at once. */
-__device__ __forceinline__ void record_done(const TraceArgs & A, unsigned long long ray,
-    int & owed)
-{
-        const int chunk = (int)(ray >> A.chunk_shift);
-        if ((owed >= 0) && (((owed >> 8) != chunk) || ((owed & 0xff) == 0xff))) {
-                __threadfence();
-                atomicAdd(A.chunk_done + (owed >> 8), (unsigned)(owed & 0xff));
-                owed = -1;
-        }
-        owed = (owed >= 0) ? owed + 1 : ((chunk << 8) | 1);
-}
-
+/* Streamed calls: a record must be visible before it is counted for its chunk. The fence
+ * that guarantees it stalls the whole warp, so counts are deferred: a lane remembers what
+ * it owes (chunk in the high bits, number of rays in the low 8) and the warp settles its
+ * debts with ONE fence -- every 128 iterations, when it runs dry, or when a lane would owe
+ * to two chunks. The records are stored by other lanes of the warp than the one that owes
+ * (warp-cooperative write-out below): every lane fences its own stores, the warp
+ * synchronises, then the owners count. Warp uniform. */
 __device__ __forceinline__ void settle_done(const TraceArgs & A, int & owed)
 {
         if (__any_sync(0xffffffffu, owed >= 0)) {
                 __threadfence();
+                __syncwarp();
                 if (owed >= 0) atomicAdd(A.chunk_done + (owed >> 8), (unsigned)(owed & 0xff));
                 owed = -1;
         }
@@ -185,6 +177,47 @@ __global__ void __launch_bounds__(128, MINB)
 
         for (;;) {
                 if (STREAM && ((++iteration & 127u) == 0u)) settle_done(A, owed);
+                /* ---- write out finished rays, one 96-byte record per instruction -------
+                 * A finished lane has left its record in shared memory (MODE_DONE). Twelve
+                 * lanes store its twelve 8-byte fields side by side: three full sectors in
+                 * one request instead of twelve partial ones from one lane -- what makes
+                 * the stores into a PEER's memory (multi-GPU) cheap
+                 * on NVLink, where every request is a packet. */
+                unsigned done_mask = __ballot_sync(FULL, mode == MODE_DONE);
+                if (done_mask != 0u) __syncwarp(); /* the records are read across lanes */
+                const bool wrote = done_mask != 0u;
+                while (done_mask != 0u) {
+                        const unsigned src = (unsigned)__ffs((int)done_mask) - 1u;
+                        done_mask &= done_mask - 1u;
+                        const unsigned t = (tid & ~31u) + src;
+                        const unsigned long long ray =
+                            ((unsigned long long)(unsigned)store.i[I_RAYHI][t] << 32) |
+                            (unsigned long long)(unsigned)store.i[I_RAYLO][t];
+                        if (lane < 12u) {
+                                unsigned long long bits;
+                                if (lane < 9u) {
+                                        const int row = (lane < 3u) ? (int)(F_POS + lane) :
+                                            ((lane == 3u) ? (int)F_ALT :
+                                                ((lane < 8u) ? (int)(F_LEN + lane - 4u) : (int)F_TOTAL));
+                                        bits = (unsigned long long)__double_as_longlong(store.f[row][t]);
+                                } else {
+                                        const int lo = (lane == 9u) ? I_NSTEPS : ((lane == 10u) ? I_IDX0 : I_HASH);
+                                        const int hi = (lane == 9u) ? I_MEDIUM0 : ((lane == 10u) ? I_IDX1 : I_NCHANGES);
+                                        bits = ((unsigned long long)(unsigned)store.i[hi][t] << 32) |
+                                            (unsigned long long)(unsigned)store.i[lo][t];
+                                }
+                                reinterpret_cast<unsigned long long *>(A.results + ray)[lane] = bits;
+                        }
+                        if (STREAM) {
+                                const int chunk = (int)(ray >> A.chunk_shift);
+                                const int o = __shfl_sync(FULL, owed, (int)src);
+                                if ((o >= 0) && (((o >> 8) != chunk) || ((o & 0xff) == 0xff)))
+                                        settle_done(A, owed);
+                                if (lane == src) owed = (owed >= 0) ? owed + 1 : ((chunk << 8) | 1);
+                        }
+                        if (lane == src) mode = MODE_IDLE;
+                }
+                if (wrote) __syncwarp(); /* ... before their columns are refilled */
                 /* ---- refill idle lanes from the global ray queue ----------
                  * An idle lane takes a ticket q (one atomicAdd per warp, ballot / popc
                  * ranks) and WAITs until ray q is on the device: at once when the whole
@@ -263,21 +296,14 @@ __global__ void __launch_bounds__(128, MINB)
                                                 tb::lla_reset(lla, G.n_transforms);
                                         }
                                         if (!finite3(pos) || !finite3(dir)) {
-                                                turtle_trace_result * R = A.results + r;
-                                                R->position[0] = pos[0];
-                                                R->position[1] = pos[1];
-                                                R->position[2] = pos[2];
-                                                R->altitude = 0.;
-                                                R->length[0] = R->length[1] = 0.;
-                                                R->length[2] = R->length[3] = 0.;
-                                                R->total = 0.;
-                                                R->n_steps = 0;
-                                                R->status = TURTLE_TRACE_INVALID;
-                                                R->index[0] = R->index[1] = -1;
-                                                R->medium_hash = 0u;
-                                                R->n_changes = 0;
-                                                if (STREAM) record_done(A, r, owed);
-                                                mode = MODE_IDLE;
+                                                /* never traced: an empty record (position
+                                                 * as given), written out with the others */
+                                                SF(F_ALT) = 0.;
+                                                SI(I_IDX0) = -1;
+                                                SI(I_IDX1) = -1;
+                                                SI(I_HASH) = 0;
+                                                SI(I_MEDIUM0) = TURTLE_TRACE_INVALID;
+                                                mode = MODE_DONE;
                                         }
                                 }
                         }
@@ -298,7 +324,7 @@ __global__ void __launch_bounds__(128, MINB)
                                 continue;
                         }
                 }
-                if ((mode == MODE_IDLE) || (mode == MODE_WAIT)) continue;
+                if ((mode == MODE_IDLE) || (mode == MODE_WAIT) || (mode == MODE_DONE)) continue;
 
                 /* ---- exactly one ECEF -> geodetic transform per lane and iteration:
                  * the one of a geometry sample, or -- local approximation on -- one of
@@ -482,27 +508,10 @@ __global__ void __launch_bounds__(128, MINB)
                         status = TURTLE_TRACE_STEPS;
 
                 if (status >= 0) {
-                        const unsigned long long ray =
-                            ((unsigned long long)(unsigned)SI(I_RAYHI) << 32) |
-                            (unsigned long long)(unsigned)SI(I_RAYLO);
-                        turtle_trace_result * R = A.results + ray;
-                        R->position[0] = SF(F_POS);
-                        R->position[1] = SF(F_POS + 1);
-                        R->position[2] = SF(F_POS + 2);
-                        R->altitude = last.alt;
-                        R->length[0] = SF(F_LEN);
-                        R->length[1] = SF(F_LEN + 1);
-                        R->length[2] = SF(F_LEN + 2);
-                        R->length[3] = SF(F_LEN + 3);
-                        R->total = total;
-                        R->n_steps = n_steps;
-                        R->status = status;
-                        R->index[0] = last.idx0;
-                        R->index[1] = last.idx1;
-                        R->medium_hash = (unsigned)SI(I_HASH);
-                        R->n_changes = SI(I_NCHANGES);
-                        if (STREAM) record_done(A, ray, owed);
-                        mode = MODE_IDLE;
+                        /* position, altitude, lengths, counters, index and hash are in the
+                         * lane store already; the status takes the row of `medium0` */
+                        SI(I_MEDIUM0) = status;
+                        mode = MODE_DONE;
                 } else {
                         SI(I_MEDIUM0) = last.idx0;
                         SF(F_DS) = tb::step_length(G, last); /* stepper.c:798-813 */
