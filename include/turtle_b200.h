@@ -176,6 +176,30 @@ TURTLE_API enum turtle_return turtle_stepper_trace_batch_device(
     const double * direction, const struct turtle_trace_rule * rule,
     struct turtle_trace_result * results, void * stream);
 
+/* ---- the stream of medium changes along every ray --------
+ * What a Monte-Carlo engine integrates over the steps -- column density, energy loss per
+ * medium, entry and exit points of the rock -- needs more than the per-medium totals of
+ * struct turtle_trace_result: it needs WHERE along the ray each medium begins. The
+ * crossings variant of the trace records, per ray, its first `max_crossings` medium changes
+ * (boundary-located by the stepper's bisection, stepper.c:832-864): the path length from
+ * the origin at which the new medium begins and the layer indices on both sides (-1 = left
+ * the data). results[i].n_changes tells how many the ray had in all; crossings
+ * [i * max_crossings + k] is valid for k < min(n_changes, max_crossings). */
+struct turtle_trace_crossing {
+        double length;
+        int32_t medium_from, medium_to;
+};
+TURTLE_API enum turtle_return turtle_stepper_trace_crossings(
+    struct turtle_plan * plan, size_t n, const double * position,
+    const double * direction, const struct turtle_trace_rule * rule,
+    struct turtle_trace_result * results, struct turtle_trace_crossing * crossings,
+    int max_crossings);
+TURTLE_API enum turtle_return turtle_stepper_trace_crossings_device(
+    struct turtle_plan * plan, size_t n, const double * position,
+    const double * direction, const struct turtle_trace_rule * rule,
+    struct turtle_trace_result * results, struct turtle_trace_crossing * crossings,
+    int max_crossings, void * stream);
+
 /* ---- one turtle_stepper_step for n independent particles -------------------
  * Same outputs as the scalar call (any output pointer may be NULL; direction
  * NULL = query mode, position untouched). `states` may be NULL: every particle

@@ -28,6 +28,7 @@ RESULT = np.dtype([
     ("position", "<f8", (3,)), ("altitude", "<f8"), ("length", "<f8", (4,)),
     ("total", "<f8"), ("n_steps", "<i4"), ("status", "<i4"), ("index", "<i4", (2,)),
     ("medium_hash", "<u4"), ("n_changes", "<i4")])
+CROSSING = np.dtype([("length", "<f8"), ("from", "<i4"), ("to", "<i4")])
 
 
 class Op(C.Structure):
@@ -70,6 +71,9 @@ def _load_driver():
     d.td_trace.restype = C.c_longlong
     d.td_trace.argtypes = [_P, C.c_size_t, _P, _P, C.POINTER(Rule), _P, C.c_int,
                            C.POINTER(C.c_double)]
+    d.td_trace_crossings.restype = C.c_longlong
+    d.td_trace_crossings.argtypes = [_P, C.c_size_t, _P, _P, C.POINTER(Rule), _P, _P, C.c_int,
+                                     C.c_int, C.POINTER(C.c_double)]
     d.td_walk.argtypes = [_P, C.c_size_t, C.c_int, _P, _P, _P, _P, _P, C.c_int,
                           C.POINTER(C.c_double)]
     d.td_step.argtypes = [_P, C.c_size_t] + [_P] * 8
@@ -166,6 +170,20 @@ class Driver:
         if steps < 0:
             raise RuntimeError("trace failed: %s" % self.d.td_last_error(self.h).decode())
         return out, steps, seconds.value
+
+    def trace_crossings(self, position, direction, rule_, max_crossings, threads=1):
+        """trace() + the first `max_crossings` medium changes of every ray."""
+        position, direction = _f8(position, (-1, 3)), _f8(direction, (-1, 3))
+        n = len(position)
+        out = np.zeros(n, dtype=RESULT)
+        cross = np.zeros((n, max_crossings), dtype=CROSSING)
+        seconds = C.c_double()
+        steps = self.d.td_trace_crossings(self.h, n, _p(position), _p(direction), C.byref(rule_),
+                                          _p(out), _p(cross), max_crossings, threads,
+                                          C.byref(seconds))
+        if steps < 0:
+            raise RuntimeError("trace failed: %s" % self.d.td_last_error(self.h).decode())
+        return out, cross
 
     def walk(self, position, direction, threads=1):
         """direction[k, i, :]: n_steps x n particles. Returns per (k, i) step, altitude, index

@@ -109,6 +109,12 @@ struct td_result {
 };
 typedef char td_result_is_96_bytes[(sizeof(struct td_result) == 96) ? 1 : -1];
 
+/* Same layout as struct turtle_trace_crossing (turtle_b200.h): one medium change. */
+struct td_crossing {
+        double length; /* path length from the origin at which the new medium begins */
+        int32_t from, to;
+};
+
 struct td_handle {
         struct api api;
         struct turtle_map * maps[TD_MAX_OBJECTS];
@@ -293,7 +299,7 @@ static int finite3(const double * v) { return isfinite(v[0]) && isfinite(v[1]) &
 
 static void trace_one(struct td_handle * h, struct turtle_stepper * s, const double * position,
     const double * direction, const struct td_rule * rule, struct td_result * R,
-    uint64_t * steps)
+    uint64_t * steps, struct td_crossing * crossings, int max_crossings)
 {
         memset(R, 0x0, sizeof(*R));
         double pos[3] = { position[0], position[1], position[2] };
@@ -331,6 +337,11 @@ static void trace_one(struct td_handle * h, struct turtle_stepper * s, const dou
                 total += step;
                 n++;
                 if (index[0] != m0) {
+                        if ((crossings != NULL) && (changes < max_crossings)) {
+                                crossings[changes].length = total;
+                                crossings[changes].from = m0;
+                                crossings[changes].to = index[0];
+                        }
                         changes++;
                         hash = (hash ^ (uint32_t)(index[0] + 1)) * 16777619u;
                 }
@@ -356,6 +367,8 @@ struct trace_job {
         struct td_result * results;
         uint64_t steps;
         int failed;
+        struct td_crossing * crossings; /* [n][max_crossings] or NULL */
+        int max_crossings;
 };
 
 static void * trace_thread(void * arg)
@@ -368,7 +381,9 @@ static void * trace_thread(void * arg)
         }
         for (size_t i = job->first; i < job->n; i += job->stride)
                 trace_one(job->h, s, job->position + 3 * i, job->direction + 3 * i, job->rule,
-                    job->results + i, &job->steps);
+                    job->results + i, &job->steps,
+                    (job->crossings != NULL) ? job->crossings + i * (size_t)job->max_crossings : NULL,
+                    job->max_crossings);
         job->h->api.stepper_destroy(&s);
         return NULL;
 }
@@ -382,9 +397,22 @@ static double now_seconds(void)
 
 /* Trace n rays on `threads` pthreads (thread t takes rays t, t+T, ...). Returns the
  * number of steps, or -1; *seconds = wall time from thread creation to join. */
+long long td_trace_crossings(struct td_handle * h, size_t n, const double * position,
+    const double * direction, const struct td_rule * rule, struct td_result * results,
+    struct td_crossing * crossings, int max_crossings, int threads, double * seconds);
+
 long long td_trace(struct td_handle * h, size_t n, const double * position,
     const double * direction, const struct td_rule * rule, struct td_result * results,
     int threads, double * seconds)
+{
+        return td_trace_crossings(h, n, position, direction, rule, results, NULL, 0, threads,
+            seconds);
+}
+
+/* ... and the first `max_crossings` medium changes of every ray. */
+long long td_trace_crossings(struct td_handle * h, size_t n, const double * position,
+    const double * direction, const struct td_rule * rule, struct td_result * results,
+    struct td_crossing * crossings, int max_crossings, int threads, double * seconds)
 {
         if (threads < 1) threads = 1;
         struct trace_job * jobs = calloc(threads, sizeof(*jobs));
@@ -392,7 +420,7 @@ long long td_trace(struct td_handle * h, size_t n, const double * position,
         const double t0 = now_seconds();
         for (int t = 0; t < threads; t++) {
                 struct trace_job j = { h, n, (size_t)t, (size_t)threads, position, direction,
-                        rule, results, 0, 0 };
+                        rule, results, 0, 0, crossings, max_crossings };
                 jobs[t] = j;
                 if (threads == 1)
                         trace_thread(&jobs[t]);

@@ -141,6 +141,9 @@ SIGNATURES = {
     # rays
     "turtle_stepper_trace_batch": (_I, [_P, _N, _P, _P, C.POINTER(TraceRule), _P]),
     "turtle_stepper_trace_batch_device": (_I, [_P, _N, _P, _P, C.POINTER(TraceRule), _P, _P]),
+    "turtle_stepper_trace_crossings": (_I, [_P, _N, _P, _P, C.POINTER(TraceRule), _P, _P, _I]),
+    "turtle_stepper_trace_crossings_device": (_I, [_P, _N, _P, _P, C.POINTER(TraceRule), _P, _P,
+                                                   _I, _P]),
     # particle steps
     "turtle_states_create": (_I, [_P, _N, _PP]),
     "turtle_states_destroy": (None, [_PP]),

@@ -18,6 +18,9 @@ TRACE_RESULT = np.dtype([
     ("medium_hash", "<u4"), ("n_changes", "<i4")])
 assert TRACE_RESULT.itemsize == 96
 
+TRACE_CROSSING = np.dtype([("length", "<f8"), ("from", "<i4"), ("to", "<i4")])
+assert TRACE_CROSSING.itemsize == 16
+
 TRACE_ALTITUDE, TRACE_DOMAIN, TRACE_LENGTH, TRACE_STEPS, TRACE_INVALID = range(5)
 
 
@@ -407,6 +410,18 @@ class Plan:
         _check(lib.turtle_stepper_trace_batch(self._p, n, _ptr(position), _ptr(direction),
                                               C.byref(rule), _ptr(results)))
         return results
+
+    def trace_crossings(self, position, direction, rule, max_crossings):
+        """turtle_stepper_trace_crossings: the trace records and, per ray, its first
+        `max_crossings` medium changes (structured array [n, max_crossings])."""
+        position, direction = _f8(position, (-1, 3)), _f8(direction, (-1, 3))
+        n = len(position)
+        results = np.zeros(n, dtype=TRACE_RESULT)
+        crossings = np.zeros((n, max_crossings), dtype=TRACE_CROSSING)
+        _check(lib.turtle_stepper_trace_crossings(
+            self._p, n, _ptr(position), _ptr(direction), C.byref(rule), _ptr(results),
+            _ptr(crossings), max_crossings))
+        return results, crossings
 
     def trace_device(self, n, position, direction, rule, results, stream=None):
         """Device tensors in / out (turtle_stepper_trace_batch_device), asynchronous."""

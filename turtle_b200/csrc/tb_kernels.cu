@@ -77,6 +77,9 @@ struct TraceArgs {
         int chunk_shift;
         const unsigned long long * watermark;
         unsigned * chunk_done;
+        /* medium changes of every ray (turtle_stepper_trace_crossings), or NULL */
+        turtle_trace_crossing * crossings;
+        int max_crossings;
 };
 
 #define STREAM_ABORT (~0ull)
@@ -491,6 +494,17 @@ __global__ void __launch_bounds__(128, MINB)
                         SI(I_NSTEPS) = n_steps;
                         my_steps++;
                         if (last.idx0 != medium0) {
+                                const int k = SI(I_NCHANGES);
+                                if ((A.crossings != NULL) && (k < A.max_crossings)) {
+                                        const unsigned long long ray =
+                                            ((unsigned long long)(unsigned)SI(I_RAYHI) << 32) |
+                                            (unsigned long long)(unsigned)SI(I_RAYLO);
+                                        turtle_trace_crossing * c = A.crossings +
+                                            ray * (unsigned long long)A.max_crossings + k;
+                                        c->length = total;
+                                        c->medium_from = medium0;
+                                        c->medium_to = last.idx0;
+                                }
                                 SI(I_NCHANGES) += 1;
                                 SI(I_HASH) = (int)(((unsigned)SI(I_HASH) ^
                                                        (unsigned)(last.idx0 + 1)) * 16777619u);
@@ -1744,7 +1758,8 @@ struct StreamState {
 static cudaError_t launch_trace(struct turtle_plan * plan, int slot, size_t n,
     const double * d_position, const double * d_direction,
     const struct turtle_trace_rule * rule, struct turtle_trace_result * d_results,
-    unsigned long long * d_counters, cudaStream_t stream, const StreamState * streamed = NULL)
+    unsigned long long * d_counters, cudaStream_t stream, const StreamState * streamed = NULL,
+    turtle_trace_crossing * d_crossings = NULL, int max_crossings = 0)
 {
         cudaError_t err = cudaMemsetAsync(d_counters, 0x0, 4 * sizeof(unsigned long long), stream);
         if (err != cudaSuccess) return err;
@@ -1753,6 +1768,8 @@ static cudaError_t launch_trace(struct turtle_plan * plan, int slot, size_t n,
         A.chunk_shift = (streamed != NULL) ? streamed->chunk_shift : 0;
         A.watermark = (streamed != NULL) ? streamed->watermark : NULL;
         A.chunk_done = (streamed != NULL) ? streamed->chunk_done : NULL;
+        A.crossings = d_crossings;
+        A.max_crossings = max_crossings;
         A.order = NULL;
         if (streamed == NULL)
                 err = schedule_rays(plan, slot, n, d_position, d_direction, stream, &A.order);
@@ -1832,6 +1849,28 @@ extern "C" enum turtle_return turtle_stepper_trace_batch_device(
         CUDA_TRY(&turtle_stepper_trace_batch_device,
             launch_trace(plan, N_SLOTS, n, position, direction, rule, results,
                 plan->d_counters + 4 * N_SLOTS, (cudaStream_t)stream));
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_stepper_trace_crossings_device(
+    struct turtle_plan * plan, size_t n, const double * position,
+    const double * direction, const struct turtle_trace_rule * rule,
+    struct turtle_trace_result * results, struct turtle_trace_crossing * crossings,
+    int max_crossings, void * stream)
+{
+        turtle_function_t * fn = FN(&turtle_stepper_trace_crossings_device);
+        enum turtle_return rc = check_rule(fn, rule);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        if ((max_crossings < 0) || ((max_crossings > 0) && (crossings == NULL)))
+                return tbh::raise(fn, TURTLE_RETURN_DOMAIN_ERROR, BATCH_CU, __LINE__,
+                    "invalid crossings buffer");
+        if (n == 0) return TURTLE_RETURN_SUCCESS;
+        CUDA_TRY(fn, cudaSetDevice(plan->device));
+        memset(&plan->counters, 0x0, sizeof(plan->counters));
+        plan->counters.rays = n;
+        CUDA_TRY(fn, launch_trace(plan, N_SLOTS, n, position, direction, rule, results,
+                         plan->d_counters + 4 * N_SLOTS, (cudaStream_t)stream, NULL,
+                         (max_crossings > 0) ? crossings : NULL, max_crossings));
         return TURTLE_RETURN_SUCCESS;
 }
 
@@ -2220,6 +2259,43 @@ struct DeviceBuffers {
                         CUDA_TRY(fn, cudaMemcpy((hptr), (dptr), (bytes),           \
                                          cudaMemcpyDeviceToHost));                 \
         } while (0)
+
+/* Host buffers: one resident launch (the crossings are a diagnostic stream, not the
+ * throughput path: no chunking). */
+extern "C" enum turtle_return turtle_stepper_trace_crossings(
+    struct turtle_plan * plan, size_t n, const double * position,
+    const double * direction, const struct turtle_trace_rule * rule,
+    struct turtle_trace_result * results, struct turtle_trace_crossing * crossings,
+    int max_crossings)
+{
+        turtle_function_t * fn = FN(&turtle_stepper_trace_crossings);
+        enum turtle_return rc = check_rule(fn, rule);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        if ((max_crossings < 0) || ((max_crossings > 0) && (crossings == NULL)))
+                return tbh::raise(fn, TURTLE_RETURN_DOMAIN_ERROR, BATCH_CU, __LINE__,
+                    "invalid crossings buffer");
+        if (n == 0) return TURTLE_RETURN_SUCCESS;
+        CUDA_TRY(fn, cudaSetDevice(plan->device));
+        DeviceBuffers buf;
+        double *d_pos, *d_dir;
+        turtle_trace_result * d_res;
+        turtle_trace_crossing * d_cross;
+        const size_t cross_bytes = n * (size_t)max_crossings * sizeof(turtle_trace_crossing);
+        CUDA_TRY(fn, buf.get((void **)&d_pos, position, n * 3 * sizeof(double), true));
+        CUDA_TRY(fn, buf.get((void **)&d_dir, direction, n * 3 * sizeof(double), true));
+        CUDA_TRY(fn, buf.get((void **)&d_res, NULL, n * sizeof(*d_res), false));
+        CUDA_TRY(fn, buf.get((void **)&d_cross, NULL, cross_bytes ? cross_bytes : 16, false));
+        CUDA_TRY(fn, cudaMemset(d_cross, 0x0, cross_bytes ? cross_bytes : 16));
+        rc = turtle_stepper_trace_crossings_device(plan, n, d_pos, d_dir, rule, d_res, d_cross,
+            max_crossings, NULL);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        CUDA_TRY(fn, cudaDeviceSynchronize());
+        turtle_plan_counters_sync(plan);
+        CUDA_TRY(fn, cudaMemcpy(results, d_res, n * sizeof(*d_res), cudaMemcpyDeviceToHost));
+        if (cross_bytes)
+                CUDA_TRY(fn, cudaMemcpy(crossings, d_cross, cross_bytes, cudaMemcpyDeviceToHost));
+        return TURTLE_RETURN_SUCCESS;
+}
 
 extern "C" enum turtle_return turtle_stepper_step_batch(struct turtle_plan * plan,
     struct turtle_states * states, size_t n, double * position,
