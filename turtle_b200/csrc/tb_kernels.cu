@@ -77,6 +77,7 @@ struct TraceArgs {
         int chunk_shift;
         const unsigned long long * watermark;
         unsigned * chunk_done;
+        unsigned * chunk_flags; /* host-mapped: chunk k is complete (set by the kernel) */
         /* medium changes of every ray (turtle_stepper_trace_crossings), or NULL */
         turtle_trace_crossing * crossings;
         int max_crossings;
@@ -104,22 +105,21 @@ __device__ __forceinline__ void settle_done(const TraceArgs & A, int & owed)
         if (__any_sync(0xffffffffu, owed >= 0)) {
                 __threadfence();
                 __syncwarp();
-                if (owed >= 0) atomicAdd(A.chunk_done + (owed >> 8), (unsigned)(owed & 0xff));
+                if (owed >= 0) {
+                        const unsigned k = (unsigned)(owed >> 8), add = (unsigned)(owed & 0xff);
+                        const unsigned before = atomicAdd(A.chunk_done + k, add);
+                        /* the count that completes a chunk tells the host, which drains
+                         * the chunks in the order they complete */
+                        const unsigned long long first = (unsigned long long)k << A.chunk_shift;
+                        const unsigned long long rest = A.n - first;
+                        const unsigned size = (rest >> A.chunk_shift) ? (1u << A.chunk_shift) :
+                                                                        (unsigned)rest;
+                        if (before + add == size) {
+                                __threadfence_system();
+                                *(volatile unsigned *)(A.chunk_flags + k) = 1u;
+                        }
+                }
                 owed = -1;
-        }
-}
-
-/* Stream-ordered wait for a chunk of results (one thread): the copy that follows it in
- * the stream finds every record of the chunk in place. */
-__global__ void wait_chunk_kernel(const unsigned * done, unsigned count,
-    const unsigned long long * watermark)
-{
-        const volatile unsigned * d = done;
-        const volatile unsigned long long * w = watermark;
-        const unsigned long long t0 = global_ns();
-        while ((*d < count) && (*w != STREAM_ABORT)) {
-                __nanosleep(2000);
-                if (global_ns() - t0 > 2ull * STREAM_TIMEOUT_NS) break; /* reported by the host */
         }
 }
 
@@ -1230,6 +1230,7 @@ struct turtle_plan {
         size_t all_rays;
         unsigned long long * d_stream_state; /* watermark + per-chunk counters */
         unsigned long long * h_marks;        /* pinned: the watermark values to copy */
+        unsigned * h_flags;                  /* pinned + mapped: chunk completion flags */
         size_t stream_chunks;
         cudaEvent_t ev_reset;
         cudaStream_t drain[4]; /* N_DRAINS result streams */
@@ -1404,6 +1405,7 @@ static enum turtle_return freeze_plan(turtle_function_t * fn, struct turtle_step
         plan->all_rays = 0;
         plan->d_stream_state = NULL;
         plan->h_marks = NULL;
+        plan->h_flags = NULL;
         plan->stream_chunks = 0;
         plan->ev_reset = NULL;
         for (int j = 0; j < 4; j++) plan->drain[j] = NULL;
@@ -1615,6 +1617,7 @@ extern "C" void turtle_plan_destroy(struct turtle_plan ** plan_)
         cudaFree(plan->d_all_out);
         cudaFree(plan->d_stream_state);
         if (plan->h_marks != NULL) cudaFreeHost(plan->h_marks);
+        if (plan->h_flags != NULL) cudaFreeHost(plan->h_flags);
         if (plan->ev_reset != NULL) cudaEventDestroy(plan->ev_reset);
         for (int j = 0; j < 4; j++)
                 if (plan->drain[j] != NULL) cudaStreamDestroy(plan->drain[j]);
@@ -1753,6 +1756,7 @@ struct StreamState {
         int chunk_shift;
         const unsigned long long * watermark;
         unsigned * chunk_done;
+        unsigned * chunk_flags;
 };
 
 static cudaError_t launch_trace(struct turtle_plan * plan, int slot, size_t n,
@@ -1768,6 +1772,7 @@ static cudaError_t launch_trace(struct turtle_plan * plan, int slot, size_t n,
         A.chunk_shift = (streamed != NULL) ? streamed->chunk_shift : 0;
         A.watermark = (streamed != NULL) ? streamed->watermark : NULL;
         A.chunk_done = (streamed != NULL) ? streamed->chunk_done : NULL;
+        A.chunk_flags = (streamed != NULL) ? streamed->chunk_flags : NULL;
         A.crossings = d_crossings;
         A.max_crossings = max_crossings;
         A.order = NULL;
@@ -1923,8 +1928,9 @@ extern "C" void turtle_plan_counters_sync(struct turtle_plan * plan)
  *   stream 0      : the trace kernel -- a lane that holds ticket q waits until the
  *                   watermark has passed q (MODE_WAIT), and every finished ray is counted
  *                   for its chunk after a __threadfence;
- *   stream 2 (D2H): for each chunk, a one-thread kernel that waits for the chunk's count,
- *                   then the copy of its records.
+ *   drain streams : the lane that counts the last ray of a chunk raises the chunk's flag in
+ *                   mapped host memory; the calling thread watches the flags and queues the
+ *                   copy of each chunk's records as it completes.
  * Compared with one kernel per chunk there is a single kernel tail instead of one per
  * chunk, and no lane ever idles between chunks. */
 static enum turtle_return trace_streamed(struct turtle_plan * plan, size_t n,
@@ -1949,13 +1955,17 @@ static enum turtle_return trace_streamed(struct turtle_plan * plan, size_t n,
         if (plan->stream_chunks < n_chunks) {
                 cudaFree(plan->d_stream_state);
                 if (plan->h_marks != NULL) cudaFreeHost(plan->h_marks);
+                if (plan->h_flags != NULL) cudaFreeHost(plan->h_flags);
                 plan->d_stream_state = NULL;
                 plan->h_marks = NULL;
+                plan->h_flags = NULL;
                 plan->stream_chunks = 0;
                 CUDA_TRY(fn, cudaMalloc((void **)&plan->d_stream_state,
                                  (n_chunks + 2) * sizeof(unsigned long long)));
                 CUDA_TRY(fn, cudaHostAlloc((void **)&plan->h_marks,
                                  (n_chunks + 1) * sizeof(unsigned long long), cudaHostAllocDefault));
+                CUDA_TRY(fn, cudaHostAlloc((void **)&plan->h_flags, n_chunks * sizeof(unsigned),
+                                 cudaHostAllocMapped));
                 plan->stream_chunks = n_chunks;
         }
         cudaStream_t compute = plan->stream[0], h2d = plan->stream[1];
@@ -1971,6 +1981,8 @@ static enum turtle_return trace_streamed(struct turtle_plan * plan, size_t n,
         st.chunk_shift = chunk_shift;
         st.watermark = plan->d_stream_state;
         st.chunk_done = (unsigned *)(plan->d_stream_state + 1);
+        CUDA_TRY(fn, cudaHostGetDevicePointer((void **)&st.chunk_flags, plan->h_flags, 0));
+        for (size_t k = 0; k < n_chunks; k++) plan->h_flags[k] = 0u;
 
         /* reset the stream state; queue the copies in; THEN start the kernel, which waits
          * for its rays. (This order also holds when kernel launches are made synchronous --
@@ -1979,8 +1991,6 @@ static enum turtle_return trace_streamed(struct turtle_plan * plan, size_t n,
                          (n_chunks + 2) * sizeof(unsigned long long), compute));
         CUDA_TRY(fn, cudaEventRecord(plan->ev_reset, compute));
         CUDA_TRY(fn, cudaStreamWaitEvent(h2d, plan->ev_reset, 0));
-        for (int j = 0; j < N_DRAINS; j++)
-                CUDA_TRY(fn, cudaStreamWaitEvent(plan->drain[j], plan->ev_reset, 0));
         plan->counters.launches = 0;
         cudaError_t err = cudaSuccess;
         for (size_t k = 0; (k < n_chunks) && (err == cudaSuccess); k++) {
@@ -2005,22 +2015,39 @@ static enum turtle_return trace_streamed(struct turtle_plan * plan, size_t n,
         err = launch_trace(plan, 0, n, d_pos, d_dir, rule, plan->d_all_out, d_counters, compute,
             &st);
         if (err == cudaSuccess) err = cudaEventRecord(plan->ev1[0], compute);
-        /* from here on a failure must release the waiters before it is reported */
-        /* chunks do not complete in order (a chunk waits for its longest ray): the drains
-         * are dealt round robin to N_DRAINS streams, so that a late chunk only holds back
-         * the chunks queued behind it on its own stream */
-        for (size_t k = 0; (k < n_chunks) && (err == cudaSuccess); k++) {
-                const size_t i0 = k * chunk;
-                const size_t m = std::min(chunk, n - i0);
-                cudaStream_t out = plan->drain[k % N_DRAINS];
-                wait_chunk_kernel<<<1, 1, 0, out>>>(st.chunk_done + k, (unsigned)m, st.watermark);
-                plan->counters.launches++;
-                err = cudaGetLastError();
-                if (err == cudaSuccess)
+        /* Drain the chunks in the order they COMPLETE (a chunk waits for its longest ray:
+         * the first chunks of a fan sorted longest-first complete late): the thread that
+         * counts the last ray of a chunk raises its flag in mapped host memory, this thread
+         * watches the flags and queues the copies, round robin on N_DRAINS streams. */
+        std::vector<char> drained(n_chunks, 0);
+        size_t remaining = n_chunks;
+        bool kernel_over = false;
+        while ((remaining > 0) && (err == cudaSuccess)) {
+                bool progress = false;
+                for (size_t k = 0; (k < n_chunks) && (err == cudaSuccess); k++) {
+                        if (drained[k]) continue;
+                        if (!kernel_over && (*(volatile unsigned *)(plan->h_flags + k) == 0u))
+                                continue;
+                        const size_t i0 = k * chunk;
+                        const size_t m = std::min(chunk, n - i0);
                         err = cudaMemcpyAsync(results + i0, plan->d_all_out + i0,
-                            m * sizeof(turtle_trace_result), cudaMemcpyDeviceToHost, out);
+                            m * sizeof(turtle_trace_result), cudaMemcpyDeviceToHost,
+                            plan->drain[(n_chunks - remaining) % N_DRAINS]);
+                        drained[k] = 1;
+                        remaining--;
+                        progress = true;
+                }
+                if (!progress && !kernel_over) {
+                        /* a finished kernel has completed every chunk (or timed out, which
+                         * is reported below): whatever is left is copied at once */
+                        const cudaError_t q = cudaStreamQuery(compute);
+                        if (q == cudaSuccess)
+                                kernel_over = true;
+                        else if (q != cudaErrorNotReady)
+                                err = q;
+                }
         }
-        if (err != cudaSuccess) { /* wake every waiter up, drain, then report */
+        if (err != cudaSuccess) { /* wake every waiting lane up, drain, then report */
                 plan->h_marks[n_chunks] = STREAM_ABORT;
                 cudaStreamSynchronize(h2d);
                 cudaMemcpyAsync(plan->d_stream_state, &plan->h_marks[n_chunks],
