@@ -342,6 +342,9 @@ __global__ void __launch_bounds__(128, MINB)
                         mode = MODE_REBUILD;
                 }
                 tb::Sample S;
+                /* SHAPE_STACK leaves registers free: the sampled position stays in them, it
+                 * IS the new position of a tentative step (same expression, same bits) */
+                double moved[3] = { 0., 0., 0. };
                 if (SHAPE == tb::SHAPE_STACK) {
                         /* one layer, one uniform geodetic stack: no list walk */
                         double p[3] = { SF(F_POS), SF(F_POS + 1), SF(F_POS + 2) };
@@ -353,6 +356,9 @@ __global__ void __launch_bounds__(128, MINB)
                                 p[2] += SF(F_DIR + 2) * step;
                         }
                         tb::sample_single_stack(G, p, S);
+                        moved[0] = p[0];
+                        moved[1] = p[1];
+                        moved[2] = p[2];
                 } else {
                         double p[3];
                         int rb_t = 0, rb_axis = 0;
@@ -429,9 +435,15 @@ __global__ void __launch_bounds__(128, MINB)
                         settle = true;
                 } else if (mode == MODE_TENT) {
                         /* position += direction * ds, stepper.c:824 */
-                        SF(F_POS) += SF(F_DIR) * ds;
-                        SF(F_POS + 1) += SF(F_DIR + 1) * ds;
-                        SF(F_POS + 2) += SF(F_DIR + 2) * ds;
+                        if (SHAPE == tb::SHAPE_STACK) {
+                                SF(F_POS) = moved[0];
+                                SF(F_POS + 1) = moved[1];
+                                SF(F_POS + 2) = moved[2];
+                        } else {
+                                SF(F_POS) += SF(F_DIR) * ds;
+                                SF(F_POS + 1) += SF(F_DIR + 1) * ds;
+                                SF(F_POS + 2) += SF(F_DIR + 2) * ds;
+                        }
                         publish = true;
                         if (S.idx0 != medium0) { /* stepper.c:832-838 */
                                 SF(F_DS0) = -ds;
@@ -474,13 +486,13 @@ __global__ void __launch_bounds__(128, MINB)
                 }
                 if (!settle) continue;
 
-                tb::Sample last;
+                tb::Sample last; /* stepper->last: this sample, or the one published before */
                 last.lat = last.lon = 0.;
-                last.alt = SF(F_ALT);
-                last.elev0 = SF(F_ELEV0);
-                last.elev1 = SF(F_ELEV1);
-                last.idx0 = SI(I_IDX0);
-                last.idx1 = SI(I_IDX1);
+                last.alt = publish ? S.alt : SF(F_ALT);
+                last.elev0 = publish ? S.elev0 : SF(F_ELEV0);
+                last.elev1 = publish ? S.elev1 : SF(F_ELEV1);
+                last.idx0 = publish ? S.idx0 : SI(I_IDX0);
+                last.idx1 = publish ? S.idx1 : SI(I_IDX1);
                 double total = SF(F_TOTAL);
                 int n_steps = SI(I_NSTEPS);
                 if (mode != MODE_INIT) {
