@@ -1236,6 +1236,39 @@ enum turtle_return tbh::stepper_flatten(struct turtle_stepper * s,
         return rc;
 }
 
+/* Geodetic footprint of a projected map (tb::DataDesc::box): the border of the map is
+ * walked node by node through the inverse projection; the box is widened by 1E-06 deg
+ * (0.1 m) and dropped when the footprint wraps in longitude or is not finite. */
+static void map_geodetic_box(const struct turtle_map * m, const tb::ProjDesc & P, tb::DataDesc & d)
+{
+        d.boxed = 0;
+        d.box[0] = d.box[1] = d.box[2] = d.box[3] = 0.;
+        if ((P.type == tb::PROJ_GEODETIC) || (m->nx < 2) || (m->ny < 2)) return;
+        double la0 = DBL_MAX, la1 = -DBL_MAX, lo0 = DBL_MAX, lo1 = -DBL_MAX;
+        const double x1 = m->x0 + m->dx * (m->nx - 1), y1 = m->y0 + m->dy * (m->ny - 1);
+        for (int side = 0; side < 4; side++) {
+                const int n = (side < 2) ? m->nx : m->ny;
+                for (int k = 0; k < n; k++) {
+                        const double x = (side < 2) ? m->x0 + k * m->dx : ((side == 2) ? m->x0 : x1);
+                        const double y = (side < 2) ? ((side == 0) ? m->y0 : y1) : m->y0 + k * m->dy;
+                        double la, lo;
+                        tb::unproject(P, x, y, la, lo);
+                        if (!isfinite(la) || !isfinite(lo)) return;
+                        la0 = std::min(la0, la);
+                        la1 = std::max(la1, la);
+                        lo0 = std::min(lo0, lo);
+                        lo1 = std::max(lo1, lo);
+                }
+        }
+        if ((lo1 - lo0 > 90.) || (la1 > 89.) || (la0 < -89.)) return;
+        const double margin = 1E-06;
+        d.box[0] = la0 - margin;
+        d.box[1] = la1 + margin;
+        d.box[2] = lo0 - margin;
+        d.box[3] = lo1 + margin;
+        d.boxed = 1;
+}
+
 /* Does the closed footprint of a tile meet the region of a residency plan? */
 static int tile_in_region(const tb::MapDesc & t, const struct turtle_residency * r)
 {
@@ -1298,6 +1331,7 @@ enum turtle_return tbh::flatten_into(struct turtle_stepper * s, tb_flat_geometry
                         F.maps.push_back(map_desc(d.map));
                         F.src.push_back(d.map);
                         F.file.push_back(std::string());
+                        map_geodetic_box(d.map, G.transforms[d.transform], G.data[i]);
                 } else if (d.kind == tb::DATA_STACK) {
                         struct turtle_stack * st = d.stack;
                         if (load_tiles) {
