@@ -48,19 +48,19 @@ N_AZ = N_EL = 4096
 # FP64-pipe work per geodetic-stack sample (DFMA / DMUL / DADD / DSETP, one FMA = 1), in
 # lane slots of the pipe -- a warp instruction occupies 32 of them whatever its active mask:
 #   OPS_PER_SAMPLE      what the CURRENT kernel executes, from the committed ncu capture
-#                       (profiles/r01g_trace_kernel_ncu_full.md: FP64-pipe warp instructions
+#                       (profiles/r01i_trace_kernel_ncu_full.md: FP64-pipe warp instructions
 #                       x 32 / samples). This is the roofline numerator: the smallest
 #                       instruction count known to compute the reference's expressions bit
 #                       for bit (exact divisions sharing reciprocals, own asin / atan2).
 #   NAIVE_OPS_PER_SAMPLE the straightforward expansion (IEEE divisions, library sqrt / asin /
 #                       atan2) measured on the first kernel of this round
 #                       (profiles/r01_trace_kernel_ncu_full.md); reported for reference only.
-OPS_PER_SAMPLE = 270.0
+OPS_PER_SAMPLE = 264.0
 NAIVE_OPS_PER_SAMPLE = 382.0
 BYTES_PER_RAY = 48 + 96  # position + direction in, result record out
 BYTES_PER_SAMPLE = 8     # four 16-bit nodes
-# DRAM traffic of one 16 Mi-ray launch (ncu --set full, profiles/r01g_trace_kernel_ncu_full.md)
-DRAM_BYTES_PER_LAUNCH = 7.9e9
+# DRAM traffic of one 16 Mi-ray launch (ncu --set full, profiles/r01i_trace_kernel_ncu_full.md)
+DRAM_BYTES_PER_LAUNCH = 9.18e9
 
 
 def stack_dir():
@@ -404,11 +404,11 @@ def main():
         "peak_source": "turtle_b200_dfma_peak() measured in this run (MEASURED_PEAKS.json has "
                        "no FP64 entry; nominal 148 SM x 64 / clk x 1.965 GHz = 18.6)",
         "ops_per_sample": OPS_PER_SAMPLE, "samples_per_launch": samples,
-        "ops_source": "executed by this kernel (ncu, profiles/r01g_trace_kernel_ncu_full.md)",
+        "ops_source": "executed by this kernel (ncu, profiles/r01i_trace_kernel_ncu_full.md)",
         "naive_ops_per_sample": NAIVE_OPS_PER_SAMPLE,
         "kernel_ms": kernel_ms, "traffic": DRAM_BYTES_PER_LAUNCH,
         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu "
-                          "--set full (profiles/r01g_trace_kernel_ncu_full.md)",
+                          "--set full (profiles/r01i_trace_kernel_ncu_full.md)",
         "hbm": {"achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak,
                 "unit": "GB/s", "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
                 "algorithmic_bytes": alg_bytes, "peak_source": hbm_src},
