@@ -2860,6 +2860,15 @@ extern "C" const char * tb_batch_function_name(turtle_function_t * caller)
         NAME(turtle_projection_unproject_batch_device);
         NAME(turtle_map_gradient_batch);
         NAME(turtle_map_gradient_batch_device);
+        NAME(turtle_stepper_freeze_region);
+        NAME(turtle_residency_from_rays);
+        NAME(turtle_stepper_trace_crossings);
+        NAME(turtle_stepper_trace_crossings_device);
+        NAME(turtle_b200_peer_alloc);
+        NAME(turtle_b200_peer_free);
+        NAME(turtle_b200_peer_export);
+        NAME(turtle_b200_peer_open);
+        NAME(turtle_b200_peer_close);
 #undef NAME
         return NULL;
 }
