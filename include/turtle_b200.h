@@ -312,6 +312,20 @@ TURTLE_API const char * turtle_b200_version(void);
  * differ in any bit (0 expected), -1 without a device. */
 TURTLE_API long long turtle_b200_selftest_division(size_t n, uint64_t seed);
 
+/* ---- resampling a geometry into a map ---------------------
+ * The step that PRODUCES a high-resolution local map: examples/example-projection.c:88-104
+ * walks the nodes of a projected map, un-projects each one, asks the tile stack for its
+ * elevation and fills the node -- one scalar call chain per node. Here a kernel does it
+ * for all nodes: node (x, y) -> inverse projection of `map` -> (latitude, longitude) ->
+ * ground elevation of layer `layer` of the plan's geometry (the first data of the layer,
+ * in the stepper's priority order, that holds the point, plus its offset; no geoid
+ * undulation: the data's own datum) -> turtle_map_fill semantics for the node (quantised
+ * to the map's 16-bit scale; TURTLE_RETURN_DOMAIN_ERROR if a value is outside of the
+ * map's z span). Nodes where the layer has no data are left as they are and counted in
+ * *outside (may be NULL). */
+TURTLE_API enum turtle_return turtle_map_resample(struct turtle_map * map,
+    struct turtle_plan * plan, int layer, size_t * outside);
+
 /* ---- multi-GPU: result records written straight into a peer GPU's memory ----------
  * Rays shard across the GPUs of a box with the DEM replicated;
  * the only exchange of the path is the delivery of the fixed-size result records to the

@@ -193,6 +193,14 @@ class Map:
         lib.turtle_map_meta(self._p, C.byref(info), C.byref(name))
         return info, (name.value.decode() if name.value else None)
 
+    def resample(self, plan, layer=0):
+        """turtle_map_resample: fill every node from layer `layer` of the plan's geometry
+        (example-projection.c:88-104 as one kernel). Returns the number of nodes the
+        geometry has no data for (left untouched)."""
+        outside = C.c_size_t()
+        _check(lib.turtle_map_resample(self._p, plan.handle, layer, C.byref(outside)))
+        return outside.value
+
     def dump(self, path):
         """turtle_map_dump: `.png` (any map) or `.tif` (integer metre scale, geodetic)."""
         _check(lib.turtle_map_dump(self._p, path.encode()))

@@ -978,6 +978,46 @@ __global__ void position_kernel(const __grid_constant__ tb::Geometry G,
         }
 }
 
+/* Ground elevation of one layer at the nodes of a grid (turtle_map_resample): node ->
+ * inverse projection -> the layer's first data that holds the point (the elevation rule
+ * of stepper.c:266-324, without the geoid). */
+__global__ void __launch_bounds__(256) resample_kernel(const __grid_constant__ tb::Geometry G,
+    const tb::ProjDesc P, int nx, int ny, double x0, double dx, double y0, double dy,
+    int layer_index, double * __restrict__ z_out, int * __restrict__ inside_out)
+{
+        const size_t total = (size_t)nx * (size_t)ny;
+        const size_t stride = (size_t)gridDim.x * blockDim.x;
+        const tb::LayerDesc layer = G.layers[layer_index];
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+                const int iy = (int)(i / (size_t)nx);
+                const int ix = (int)(i - (size_t)iy * nx);
+                const double x = x0 + ix * dx, y = y0 + iy * dy; /* map.c:219-220 */
+                double la = y, lo = x;
+                if (P.type != tb::PROJ_GEODETIC) tb::unproject(P, x, y, la, lo);
+                int found = 0;
+                double z = 0.;
+                for (int k = 0; (k < layer.n) && !found; k++) {
+                        const tb::MetaDesc & meta = G.metas[layer.first + k];
+                        const tb::DataDesc & d = G.data[meta.data];
+                        if (d.kind == tb::DATA_FLAT) {
+                                found = 1;
+                                z = 0.;
+                        } else if (d.kind == tb::DATA_STACK) {
+                                found = tb::stack_elevation(G, G.stacks[d.ref], la, lo, z);
+                        } else if (G.transforms[d.transform].type != tb::PROJ_GEODETIC) {
+                                double mx, my;
+                                tb::project(G.transforms[d.transform], la, lo, mx, my);
+                                found = tb::map_elevation(G.maps[d.ref], mx, my, z);
+                        } else {
+                                found = tb::map_elevation(G.maps[d.ref], lo, la, z);
+                        }
+                        if (found) z += meta.offset;
+                }
+                z_out[i] = z;
+                inside_out[i] = found;
+        }
+}
+
 /* ---- frame transform kernels (ref: ecef.c) -------------------------------- */
 
 __global__ void __launch_bounds__(256) to_geodetic_kernel(unsigned long long n,
@@ -2336,6 +2376,46 @@ extern "C" enum turtle_return turtle_stepper_trace_crossings(
         return TURTLE_RETURN_SUCCESS;
 }
 
+extern "C" enum turtle_return turtle_map_resample(struct turtle_map * map,
+    struct turtle_plan * plan, int layer, size_t * outside)
+{
+        turtle_function_t * fn = FN(&turtle_map_resample);
+        if (outside != NULL) *outside = 0;
+        if ((layer < 0) || (layer >= plan->G.n_layers))
+                return tbh::raise(fn, TURTLE_RETURN_DOMAIN_ERROR, BATCH_CU, __LINE__,
+                    "invalid layer index");
+        CUDA_TRY(fn, cudaSetDevice(plan->device));
+        tb::ProjDesc P;
+        tbh::projection_to_desc(&map->projection, &P);
+        const size_t n = (size_t)map->nx * map->ny;
+        DeviceBuffers buf;
+        double * d_z;
+        int * d_inside;
+        CUDA_TRY(fn, buf.get((void **)&d_z, NULL, n * sizeof(double), false));
+        CUDA_TRY(fn, buf.get((void **)&d_inside, NULL, n * sizeof(int), false));
+        const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)plan->sm_count * 8);
+        resample_kernel<<<blocks, 256>>>(plan->G, P, map->nx, map->ny, map->x0, map->dx, map->y0,
+            map->dy, layer, d_z, d_inside);
+        CUDA_TRY(fn, cudaGetLastError());
+        std::vector<double> z(n);
+        std::vector<int> inside(n);
+        CUDA_TRY(fn, cudaMemcpy(z.data(), d_z, n * sizeof(double), cudaMemcpyDeviceToHost));
+        CUDA_TRY(fn, cudaMemcpy(inside.data(), d_inside, n * sizeof(int), cudaMemcpyDeviceToHost));
+        size_t missing = 0;
+        for (int iy = 0; iy < map->ny; iy++)
+                for (int ix = 0; ix < map->nx; ix++) {
+                        const size_t i = (size_t)iy * map->nx + ix;
+                        if (!inside[i]) {
+                                missing++;
+                                continue;
+                        }
+                        const enum turtle_return rc = turtle_map_fill(map, ix, iy, z[i]);
+                        if (rc != TURTLE_RETURN_SUCCESS) return rc; /* raised by turtle_map_fill */
+                }
+        if (outside != NULL) *outside = missing;
+        return TURTLE_RETURN_SUCCESS;
+}
+
 extern "C" enum turtle_return turtle_stepper_step_batch(struct turtle_plan * plan,
     struct turtle_states * states, size_t n, double * position,
     const double * direction, double * latitude, double * longitude,
@@ -2861,6 +2941,7 @@ extern "C" const char * tb_batch_function_name(turtle_function_t * caller)
         NAME(turtle_map_gradient_batch);
         NAME(turtle_map_gradient_batch_device);
         NAME(turtle_stepper_freeze_region);
+        NAME(turtle_map_resample);
         NAME(turtle_residency_from_rays);
         NAME(turtle_stepper_trace_crossings);
         NAME(turtle_stepper_trace_crossings_device);
