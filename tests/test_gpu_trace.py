@@ -156,6 +156,10 @@ def test_determinism_and_chunking(small_stack):
     c = plan.trace(pos, dirs, rule)
     assert a.tobytes() == c.tobytes()
     plan.schedule_set(0)
+    os.environ["TURTLE_B200_STREAM_MAX_RAYS"] = str(1 << 20)  # two streamed rounds
+    c = plan.trace(pos, dirs, rule)
+    del os.environ["TURTLE_B200_STREAM_MAX_RAYS"]
+    assert a.tobytes() == c.tobytes() and plan.counters()["rays"] == n
     plan.pipeline_set(1)    # one kernel per chunk instead of the streamed single kernel
     c = plan.trace(pos, dirs, rule)
     assert a.tobytes() == c.tobytes()

@@ -1248,6 +1248,7 @@ const size_t CHUNK_RAYS = 1u << 20; /* rays per pipeline chunk (one kernel per c
 const int STREAM_CHUNK_SHIFT = 18;  /* rays per copy of a streamed call: 256 Ki */
 const size_t STREAM_CHUNK_RAYS = (size_t)1 << STREAM_CHUNK_SHIFT;
 const int N_DRAINS = 4;             /* result streams of a streamed call */
+const size_t STREAM_MAX_RAYS = (size_t)1 << 25; /* rays per round of a streamed call */
 }
 
 struct turtle_plan {
@@ -2136,10 +2137,31 @@ extern "C" enum turtle_return turtle_stepper_trace_batch(
         memset(&plan->counters, 0x0, sizeof(plan->counters));
         if (n == 0) return TURTLE_RETURN_SUCCESS;
         CUDA_TRY(&turtle_stepper_trace_batch, cudaSetDevice(plan->device));
-        /* more than one chunk, caller's ray order: stream the batch through one kernel */
-        if ((plan->schedule == 0) && (plan->pipeline_mode != 1) && (n > STREAM_CHUNK_RAYS))
-                return trace_streamed(plan, n, position, direction, rule, results,
-                    STREAM_CHUNK_SHIFT);
+        /* more than one chunk, caller's ray order: stream the batch through one kernel --
+         * in rounds of at most STREAM_MAX_RAYS rays, which bounds the device staging of a
+         * call (144 bytes per ray) to 4.6 GB whatever the size of the batch */
+        if ((plan->schedule == 0) && (plan->pipeline_mode != 1) && (n > STREAM_CHUNK_RAYS)) {
+                turtle_plan_counters sum;
+                memset(&sum, 0x0, sizeof(sum));
+                size_t round_rays = STREAM_MAX_RAYS;
+                if (getenv("TURTLE_B200_STREAM_MAX_RAYS") != NULL) { /* tests: small rounds */
+                        const long long v = atoll(getenv("TURTLE_B200_STREAM_MAX_RAYS"));
+                        if (v >= (long long)STREAM_CHUNK_RAYS) round_rays = (size_t)v;
+                }
+                for (size_t first = 0; first < n; first += round_rays) {
+                        const size_t m = std::min(round_rays, n - first);
+                        rc = trace_streamed(plan, m, position + 3 * first, direction + 3 * first,
+                            rule, results + first, STREAM_CHUNK_SHIFT);
+                        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+                        sum.rays += plan->counters.rays;
+                        sum.steps += plan->counters.steps;
+                        sum.samples += plan->counters.samples;
+                        sum.launches += plan->counters.launches;
+                        sum.kernel_ms += plan->counters.kernel_ms;
+                }
+                plan->counters = sum;
+                return TURTLE_RETURN_SUCCESS;
+        }
         size_t chunk_rays = CHUNK_RAYS;
         if (getenv("TURTLE_B200_CHUNK_RAYS") != NULL) { /* development: pipeline sweep */
                 const long long v = atoll(getenv("TURTLE_B200_CHUNK_RAYS"));
