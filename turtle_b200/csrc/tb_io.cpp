@@ -22,6 +22,8 @@
 #include <string.h>
 #include <zlib.h>
 
+#include <exception>
+
 #include "tb_core.cuh"
 
 namespace tbio {
@@ -866,15 +868,33 @@ static int dispatch(const char * path, Header & h, RawLayout * layout,
         return rc;
 }
 
+/* A corrupt header can ask for any amount of memory: allocation failures inside a reader
+ * are reported like the reference reports its failed malloc (map.c:131-135), they do not
+ * cross the C ABI as exceptions. */
+static int guarded(const char * path, Header & h, RawLayout * layout,
+    std::vector<uint16_t> * raw, Error & error)
+{
+        try {
+                const int rc = dispatch(path, h, layout, raw, error);
+                if ((rc == 0) && ((h.nx <= 0) || (h.ny <= 0)))
+                        return fail(error, TURTLE_RETURN_BAD_FORMAT, "src/turtle/io.c",
+                            "invalid grid size in file `%s'", path);
+                return rc;
+        } catch (const std::exception &) {
+                return fail(error, TURTLE_RETURN_MEMORY_ERROR, "src/turtle/map.c",
+                    "could not allocate memory for map `%s'", path);
+        }
+}
+
 int read_header(const char * path, Header & header, Error & error)
 {
-        return dispatch(path, header, NULL, NULL, error);
+        return guarded(path, header, NULL, NULL, error);
 }
 
 int read_map(const char * path, Header & header, RawLayout & layout,
     std::vector<uint16_t> & raw, Error & error)
 {
-        return dispatch(path, header, &layout, &raw, error);
+        return guarded(path, header, &layout, &raw, error);
 }
 
 void normalise(const Header & h, const RawLayout & layout, std::vector<uint16_t> & raw)
