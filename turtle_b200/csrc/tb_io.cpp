@@ -383,6 +383,9 @@ static int png_read(const char * path, Header & h, RawLayout * layout,
 
         const size_t stride = 2 * (size_t)h.nx;
         std::vector<uint8_t> px;
+        if ((double)(stride + 1) * (double)h.ny > 1100. * (double)idat.size() + 65536.)
+                return fail(error, TURTLE_RETURN_BAD_FORMAT, PNG_C,
+                    "a libpng error occured when loading file `%s'", path);
         if ((inflate_all(idat.data(), idat.size(), px, (stride + 1) * h.ny) != 0) ||
             (px.size() < (stride + 1) * (size_t)h.ny))
                 return fail(error, TURTLE_RETURN_BAD_FORMAT, PNG_C,
@@ -615,6 +618,10 @@ static int tif_read(const char * path, Header & h, RawLayout * layout,
             !((compression == 1) || (compression == 8) || (compression == 32946)))
                 return fail(error, TURTLE_RETURN_BAD_FORMAT, TIF_C, bad, path);
         if (rows_per_strip == 0) rows_per_strip = height;
+        /* (deflate expands at most ~1032 times: a grid no file of this size can hold is a
+         * corrupt header, not a request for memory) */
+        if ((double)h.nx * (double)h.ny * 2. > 1100. * (double)f.size() + 65536.)
+                return fail(error, TURTLE_RETURN_BAD_FORMAT, TIF_C, bad, path);
         raw->assign((size_t)h.nx * h.ny, 0);
         const size_t stride = 2 * (size_t)h.nx;
         std::vector<uint8_t> plain;
