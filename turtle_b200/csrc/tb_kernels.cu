@@ -2309,14 +2309,21 @@ extern "C" enum turtle_return turtle_stepper_step_batch_device(
         bool proj = false;
         for (int t = 0; t < plan->G.n_transforms; t++)
                 if (plan->G.transforms[t].type != tb::PROJ_GEODETIC) proj = true;
-        if (lla && proj)
-                walk_kernel<true, true><<<blocks, threads, 0, st>>>(plan->G, A);
-        else if (lla)
-                walk_kernel<true, false><<<blocks, threads, 0, st>>>(plan->G, A);
-        else if (proj)
-                walk_kernel<false, true><<<blocks, threads, 0, st>>>(plan->G, A);
-        else
-                walk_kernel<false, false><<<blocks, threads, 0, st>>>(plan->G, A);
+        /* the 5 CTAs per SM get the carve-out they need and no more: the rest is L1 for the
+         * DEM gathers (as for the trace kernel) */
+        void (*kernel)(const tb::Geometry, const StepArgs) =
+            (lla && proj) ? walk_kernel<true, true> :
+            (lla ? walk_kernel<true, false> :
+                   (proj ? walk_kernel<false, true> : walk_kernel<false, false>));
+        cudaFuncAttributes attr;
+        if (cudaFuncGetAttributes(&attr, kernel) == cudaSuccess) {
+                const size_t need = 5 * (attr.sharedSizeBytes + 1024);
+                int percent = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+                if (percent > 100) percent = 100;
+                cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
+        }
+        cudaGetLastError();
+        kernel<<<blocks, threads, 0, st>>>(plan->G, A);
         plan->counters.launches++;
         plan->counters.rays = n;
         plan->counters.steps = (direction != NULL) ? n : 0;
