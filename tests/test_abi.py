@@ -40,6 +40,22 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.SIGNATURES) == declared_symbols()
 
 
+def test_headers_are_plain_c99_and_cxx(tmp_path):
+    """Both headers compile as pedantic C99 and as C++11, and the record layouts have the
+    sizes the Python mirror assumes."""
+    import subprocess
+    src = ('#include "turtle.h"\n#include "turtle_b200.h"\n'
+           'int main(void) { return ((sizeof(struct turtle_trace_result) == 96) && '
+           '(sizeof(struct turtle_trace_crossing) == 16) && '
+           '(sizeof(struct turtle_trace_rule) == 32)) ? 0 : 1; }\n')
+    for compiler, std, lang in (("gcc", "-std=c99", "c"), ("g++", "-std=c++11", "c++")):
+        exe = str(tmp_path / ("hdr_" + lang.replace("+", "x")))
+        subprocess.run([compiler, std, "-Wall", "-Wextra", "-pedantic", "-Werror",
+                        "-I" + os.path.join(ROOT, "include"), "-x", lang, "-", "-o", exe],
+                       input=src, text=True, check=True)
+        assert subprocess.run([exe]).returncode == 0
+
+
 def test_no_torch_types_in_the_abi():
     for header in ("turtle.h", "turtle_b200.h"):
         text = open(os.path.join(ROOT, "include", header)).read()
