@@ -300,6 +300,10 @@ TURTLE_API enum turtle_return turtle_map_fill_batch(
 TURTLE_API enum turtle_return turtle_map_fill_rows(
     struct turtle_map * map, int iy0, int n_rows, const double * elevation);
 
+/* Number of tiles of `stack` currently held on the HOST (what the reference's tests read
+ * from `stack->tiles.size`, stack.h:34-52 -- the type is opaque here). */
+TURTLE_API int turtle_stack_tiles_loaded(const struct turtle_stack * stack);
+
 /* ---- device utilities -------------------------------------------------------*/
 /* Number of CUDA devices visible (0 when there is no driver / GPU). */
 TURTLE_API int turtle_b200_device_count(void);

@@ -128,6 +128,7 @@ SIGNATURES = {
     "turtle_plan_schedule_set": (None, [_P, _I]),
     "turtle_plan_specialise_set": (None, [_P, _I]),
     "turtle_plan_pipeline_set": (None, [_P, _I]),
+    "turtle_stack_tiles_loaded": (_I, [_P]),
     "turtle_map_resample": (_I, [_P, _P, _I, C.POINTER(C.c_size_t)]),
     "turtle_stepper_freeze_region": (_I, [_P, _I, C.POINTER(Residency), _PP]),
     "turtle_plan_residency_get": (None, [_P, C.POINTER(ResidencyReport)]),

@@ -737,6 +737,11 @@ static void stack_drop(struct turtle_stack * stack, int cell)
         turtle_map_destroy(&m);
 }
 
+extern "C" int turtle_stack_tiles_loaded(const struct turtle_stack * stack)
+{
+        return (stack == NULL) ? 0 : (int)stack->mru.size();
+}
+
 extern "C" void turtle_stack_destroy(struct turtle_stack ** stack)
 {
         if ((stack == NULL) || (*stack == NULL)) return;
@@ -972,9 +977,12 @@ extern "C" enum turtle_return turtle_client_create(
     struct turtle_client ** client, struct turtle_stack * stack)
 {
         *client = NULL;
-        if ((stack == NULL) || (stack->lock == NULL)) /* ref: client.c:41-46 */
+        if (stack == NULL) /* ref: client.c:44-53 */
                 return RAISE(&turtle_client_create, TURTLE_RETURN_BAD_ADDRESS, CLIENT_C,
-                    "invalid stack or missing lock");
+                    "invalid null stack");
+        if (stack->lock == NULL)
+                return RAISE(&turtle_client_create, TURTLE_RETURN_BAD_ADDRESS, CLIENT_C,
+                    "stack has no lock");
         *client = new (std::nothrow) turtle_client();
         if (*client == NULL)
                 return RAISE(&turtle_client_create, TURTLE_RETURN_MEMORY_ERROR, CLIENT_C,
