@@ -153,3 +153,52 @@ def test_client(data):
         r"data in `.*topography'", str(e.value))
     check(lib.turtle_client_destroy(C.byref(client)))
     lib.turtle_stack_destroy(C.byref(stack))
+
+
+def test_projection(data):
+    """tests/test-turtle.c:516-578."""
+    m = tb.Map(11, 11, (45, 46), (3, 4), (-1, 1), None)
+    assert lib.turtle_map_projection(m.handle) is None
+    m = tb.Map(path=str(data / "map.png"))
+    lib.turtle_projection_name.restype = C.c_char_p
+    assert lib.turtle_projection_name(C.c_void_p(lib.turtle_map_projection(m.handle))) == b"UTM 31N"
+    projection = C.c_void_p()
+    check(lib.turtle_projection_create(C.byref(projection), None))
+    assert lib.turtle_projection_name(projection) is None
+    for tag in ("Lambert I", "Lambert II", "Lambert IIe", "Lambert III", "Lambert IV",
+                "Lambert 93", "UTM 31N", "UTM 3.0N", "UTM 31S", "UTM 3.0S"):
+        check(lib.turtle_projection_configure(projection, tag.encode()))
+        assert lib.turtle_projection_name(projection) == tag.encode()
+        x, y, la, lo = (C.c_double() for _ in range(4))
+        check(lib.turtle_projection_project(projection, 45.5, 3.5, C.byref(x), C.byref(y)))
+        check(lib.turtle_projection_unproject(projection, x, y, C.byref(la), C.byref(lo)))
+        assert abs(la.value - 45.5) <= 1e-8 and abs(lo.value - 3.5) <= 1e-8
+    lib.turtle_projection_destroy(C.byref(projection))
+    with pytest.raises(tb.TurtleError) as e:
+        check(lib.turtle_projection_create(C.byref(projection), b"nothing"))
+    assert e.value.code == 4 and re.match(
+        r"\{ turtle_projection_create \[#[0-9]*\], src/turtle/projection.c:[0-9]* \} "
+        r"invalid projection `nothing'", str(e.value))
+
+
+def test_strfunc():
+    """tests/test-turtle.c:1216-1269: every API function has a name, a stranger has none."""
+    lib.turtle_error_function.restype = C.c_char_p
+    names = """turtle_client_clear turtle_client_create turtle_client_destroy
+        turtle_client_elevation turtle_ecef_from_geodetic turtle_ecef_from_horizontal
+        turtle_ecef_to_geodetic turtle_ecef_to_horizontal turtle_error_function
+        turtle_error_handler_get turtle_error_handler_set turtle_map_create turtle_map_destroy
+        turtle_map_dump turtle_map_elevation turtle_map_fill turtle_map_load turtle_map_meta
+        turtle_map_node turtle_map_projection turtle_projection_configure
+        turtle_projection_create turtle_projection_destroy turtle_projection_name
+        turtle_projection_project turtle_projection_unproject turtle_stack_clear
+        turtle_stack_create turtle_stack_destroy turtle_stack_elevation turtle_stack_load
+        turtle_stepper_add_flat turtle_stepper_add_layer turtle_stepper_add_map
+        turtle_stepper_add_stack turtle_stepper_create turtle_stepper_destroy
+        turtle_stepper_geoid_get turtle_stepper_geoid_set turtle_stepper_range_get
+        turtle_stepper_range_set turtle_stepper_position turtle_stepper_step""".split()
+    raw = C.CDLL(tb._lib.LIB_PATH)
+    for name in names:
+        fn = C.cast(getattr(raw, name), C.c_void_p)
+        assert lib.turtle_error_function(fn) == name.encode(), name
+    assert lib.turtle_error_function(C.cast(NOTHING, C.c_void_p)) is None
