@@ -124,7 +124,7 @@ def layered_scene(rg):
 
 def c3(args):
     scene = layered_scene(10. if args.range is None else args.range)
-    n = args.rays or (1 << 24)
+    n = args.rays or (1 << 26)  # BASELINE.json configs[2]: 64 Mi rays
     lat = B.STACK_LAT0 - 0.1 + (B.STACK_N + 0.2) * synth.random_uniform(n, 0xC3, 0)
     lon = B.STACK_LON0 - 0.1 + (B.STACK_N + 0.2) * synth.random_uniform(n, 0xC3, 1)
     alt = -500. + 5500. * synth.random_uniform(n, 0xC3, 2)
