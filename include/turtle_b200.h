@@ -94,6 +94,13 @@ struct turtle_plan_counters {
 
 /* ---- plans ---------------------------------------------------------------- */
 
+/* Threading: a plan carries the streams, staging buffers and counters of the calls made
+ * through it -- ONE batch call at a time per plan (several plans, e.g. one per host thread
+ * or per device, are independent; they share nothing but read-only tiles of their own).
+ * This is the batched form of the reference's rule "one stepper per thread"
+ * (include/turtle.h:141-149 of the reference). The `_device` variants are asynchronous on
+ * the caller's stream; the host-pointer variants return when the results are in place. */
+
 /* Upload every map / tile referenced by `stepper` to `device` and flatten the
  * geometry. Stacks are made fully resident (all tiles of the grid are loaded):
  * this replaces the reference's on-demand tile cache (ref: src/turtle/stack.c:
