@@ -71,7 +71,7 @@ def test_png_without_topography_header(tmp_path):
         tb.Map(path=str(tmp_path / "rgb.png"))
 
 
-@pytest.mark.parametrize("compression", [None, "tiff_adobe_deflate"])
+@pytest.mark.parametrize("compression", [None, "tiff_adobe_deflate", "tiff_lzw", "tiff_lzw+predictor"])
 def test_tiff_written_by_libtiff(tmp_path, compression):
     nx, ny = 47, 29
     raw = (terrain(nx, ny, 5).astype(np.int32) - 500).astype(np.int16)
@@ -83,6 +83,10 @@ def test_tiff_written_by_libtiff(tmp_path, compression):
     ifd.tagtype[33922] = 12
     path = str(tmp_path / "libtiff.tif")
     kw = dict(tiffinfo=ifd)
+    if compression and compression.endswith("+predictor"):
+        ifd[317] = 2  # horizontal differencing
+        ifd.tagtype[317] = 3
+        compression = compression.split("+")[0]
     if compression:
         kw["compression"] = compression
     Image.fromarray(raw.view(np.uint16)).save(path, **kw)

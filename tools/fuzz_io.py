@@ -11,7 +11,7 @@ random.seed(7)
 n_ok = n_err = 0
 for name in sorted(os.listdir(IO)):
     data = open(os.path.join(IO, name), "rb").read()
-    for trial in range(1500):
+    for trial in range(400):
         b = bytearray(data)
         mode = trial % 4
         if mode == 0:

@@ -530,6 +530,76 @@ struct TiffReader {
         }
 };
 
+/* TIFF LZW (compression 5): MSB-first codes of 9 to 12 bits, ClearCode 256, EndOfInformation
+ * 257, the code width growing one code early ("early change") as every libtiff-written
+ * file does. Returns 0 on success. */
+static int lzw_decode(const uint8_t * src, size_t n, std::vector<uint8_t> & out, size_t expect)
+{
+        out.clear();
+        out.reserve(expect);
+        struct Entry { int prefix; uint8_t first, last; uint16_t length; };
+        std::vector<Entry> table(4096);
+        for (int i = 0; i < 256; i++) {
+                table[i].prefix = -1;
+                table[i].first = table[i].last = (uint8_t)i;
+                table[i].length = 1;
+        }
+        int next = 258, width = 9, previous = -1;
+        uint64_t bits = 0;
+        int have = 0;
+        size_t at = 0;
+        std::vector<uint8_t> scratch;
+        for (;;) {
+                while ((have < width) && (at < n)) {
+                        bits = (bits << 8) | src[at++];
+                        have += 8;
+                }
+                if (have < width) break; /* no EOI: accept what was decoded */
+                const int code = (int)((bits >> (have - width)) & ((1u << width) - 1u));
+                have -= width;
+                if (code == 257) break;
+                if (code == 256) {
+                        next = 258;
+                        width = 9;
+                        previous = -1;
+                        continue;
+                }
+                int emit;
+                if (code < next) {
+                        emit = code;
+                } else if ((code == next) && (previous >= 0)) {
+                        emit = -1; /* previous string + its own first byte */
+                } else {
+                        return -1;
+                }
+                if (emit >= 0) {
+                        const int len = table[emit].length;
+                        const size_t base = out.size();
+                        out.resize(base + len);
+                        for (int c = emit, k = len - 1; c >= 0; c = table[c].prefix, k--)
+                                out[base + k] = table[c].last;
+                } else {
+                        const int len = table[previous].length;
+                        const size_t base = out.size();
+                        out.resize(base + len + 1);
+                        for (int c = previous, k = len - 1; c >= 0; c = table[c].prefix, k--)
+                                out[base + k] = table[c].last;
+                        out[base + len] = table[previous].first;
+                }
+                if ((previous >= 0) && (next < 4096)) {
+                        table[next].prefix = previous;
+                        table[next].first = table[previous].first;
+                        table[next].last = (emit >= 0) ? table[emit].first : table[previous].first;
+                        table[next].length = (uint16_t)(table[previous].length + 1);
+                        next++;
+                }
+                previous = code;
+                if (next + 1 >= (1 << width) && (width < 12)) width++; /* early change */
+                if (out.size() > expect + 4096) return -1;
+        }
+        return 0;
+}
+
 static int tif_read(const char * path, Header & h, RawLayout * layout,
     std::vector<uint16_t> * raw, Error & error)
 {
@@ -615,7 +685,8 @@ static int tif_read(const char * path, Header & h, RawLayout * layout,
 
         if ((bits != 16) || (samples != 1) || tiled || (h.nx <= 0) || (h.ny <= 0) ||
             offsets.empty() || (offsets.size() != counts.size()) ||
-            !((compression == 1) || (compression == 8) || (compression == 32946)))
+            !((compression == 1) || (compression == 5) || (compression == 8) ||
+                (compression == 32946)))
                 return fail(error, TURTLE_RETURN_BAD_FORMAT, TIF_C, bad, path);
         if (rows_per_strip == 0) rows_per_strip = height;
         /* (deflate expands at most ~1032 times: a grid no file of this size can hold is a
@@ -634,8 +705,10 @@ static int tif_read(const char * path, Header & h, RawLayout * layout,
                 const uint8_t * src = &f[offsets[s]];
                 size_t have = counts[s];
                 if (compression != 1) {
-                        if (inflate_all(src, have, plain, rows * stride) != 0)
-                                return fail(error, TURTLE_RETURN_BAD_FORMAT, TIF_C, bad, path);
+                        const int rc = (compression == 5) ?
+                            lzw_decode(src, have, plain, rows * stride) :
+                            inflate_all(src, have, plain, rows * stride);
+                        if (rc != 0) return fail(error, TURTLE_RETURN_BAD_FORMAT, TIF_C, bad, path);
                         src = plain.data();
                         have = plain.size();
                 }
