@@ -63,26 +63,39 @@ BYTES_PER_SAMPLE = 8     # four 16-bit nodes
 DRAM_BYTES_PER_LAUNCH = 9.18e9
 
 
+def _synth():
+    """turtle_b200/synth.py (numpy input generators) loaded as a plain module: importing
+    the PACKAGE would load libturtle_b200.so, which the reference arm must not touch."""
+    import importlib.util
+    if "turtle_b200_synth" not in sys.modules:
+        spec = importlib.util.spec_from_file_location(
+            "turtle_b200_synth", os.path.join(ROOT, "turtle_b200", "synth.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        sys.modules["turtle_b200_synth"] = mod
+    return sys.modules["turtle_b200_synth"]
+
+
 def stack_dir():
     return os.environ.get("TURTLE_BENCH_STACK", "/tmp/turtle_b200_stack3601")
 
 
 def make_stack():
-    from turtle_b200 import synth
+    synth = _synth()
     return synth.write_hgt_stack(stack_dir(), STACK_LAT0, STACK_LON0, STACK_N, STACK_N, n=3601)
 
 
 def fan(rank, world, first, count, n_az=N_AZ, n_el=N_EL):
     """Directions of rays [first, first + count) of the part of the fan traced by `rank`:
     the azimuths of the `world` ranks interleave into one fan of world * n_az azimuths."""
-    from turtle_b200 import synth
+    synth = _synth()
     return DET_LAT, DET_LON, synth.fan_directions(
         DET_LAT, DET_LON, n_az, n_el, first=first, count=count, part=rank, parts=world)
 
 
 def fan_subsample(rank, world, stride, n_total):
     """Every `stride`-th ray of the rank's part of the fan (ray index order preserved)."""
-    from turtle_b200 import synth
+    synth = _synth()
     r = np.arange(0, n_total, stride, dtype=np.int64)
     az, el = synth.fan_angles(r, N_AZ, N_EL, part=rank, parts=world)
     return synth.np_from_horizontal(np.full(len(r), DET_LAT), np.full(len(r), DET_LON), az, el)

@@ -5,6 +5,8 @@ pthread ray loop of trace_driver.c. Three libraries are of interest:
 
   REF     oracle/_ref/libturtle_ref.so  the unmodified reference (built by
           oracle/Makefile from /root/reference; travels to the GPU box prebuilt)
+  REF_FMA oracle/_ref/libturtle_ref_fma.so  the same sources built with FMA contraction:
+          the rounding-noise floor of the path (oracle/parity.py), never the checker
   PORT    oracle/liboracle.so           the plain-C restatement (turtle_oracle.c)
   PRODUCT turtle_b200/libturtle_b200.so the product's own scalar (host) calls
 
@@ -18,6 +20,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.path.join(HERE, "_ref", "libturtle_ref.so")
+# the same sources with FMA contraction: the rounding-noise floor, not an oracle
+REF_FMA = os.path.join(HERE, "_ref", "libturtle_ref_fma.so")
 PORT = os.path.join(HERE, "liboracle.so")
 PRODUCT = os.path.join(os.path.dirname(HERE), "turtle_b200", "libturtle_b200.so")
 DRIVER = os.path.join(HERE, "libtrace_driver.so")

@@ -710,19 +710,27 @@ extern "C" enum turtle_return turtle_stack_create(struct turtle_stack ** stack,
         s->latitude_n = lat_n;
         s->longitude_n = long_n;
         s->root = path;
-        s->pinned = 0;
+        *stack = s;
+        /* a directory without tiles, or whose tiles have a null span (one row or column, no
+         * pixel scale ...): an empty stack, as in the reference (stack.c:162-163) */
+        if ((lat_n == 0) || (long_n == 0)) return TURTLE_RETURN_SUCCESS;
         s->path.assign((size_t)lat_n * long_n, std::string());
         s->tile.assign((size_t)lat_n * long_n, NULL);
         tb::MapDesc none;
         memset(&none, 0x0, sizeof none);
         s->header.assign((size_t)lat_n * long_n, none);
         for (size_t i = 0; i < files.size(); i++) { /* ref: stack.c:187-190 */
-                const int ix = (int)((files[i].x0 - long_min) / long_delta);
-                const int iy = (int)((files[i].y0 - lat_min) / lat_delta);
+                const double fx = (files[i].x0 - long_min) / long_delta;
+                const double fy = (files[i].y0 - lat_min) / lat_delta;
+                if (!(fx >= 0.) || !(fx < long_n) || !(fy >= 0.) || !(fy < lat_n)) {
+                        turtle_stack_destroy(stack);
+                        return RAISE(&turtle_stack_create, TURTLE_RETURN_BAD_FORMAT, STACK_C,
+                            "tile `%s' is off the grid of the stack", files[i].path.c_str());
+                }
+                const int ix = (int)fx, iy = (int)fy;
                 s->path[(size_t)iy * long_n + ix] = files[i].path;
                 s->header[(size_t)iy * long_n + ix] = files[i].desc;
         }
-        *stack = s;
         return TURTLE_RETURN_SUCCESS;
 }
 
@@ -755,8 +763,7 @@ extern "C" enum turtle_return turtle_stack_clear(struct turtle_stack * stack)
         if ((stack->lock != NULL) && (stack->lock() != 0))
                 return RAISE(&turtle_stack_clear, TURTLE_RETURN_LOCK_ERROR, STACK_C,
                     "could not acquire the lock");
-        if (stack->pinned == 0)
-                for (size_t i = 0; i < stack->tile.size(); i++) stack_drop(stack, (int)i);
+        for (size_t i = 0; i < stack->tile.size(); i++) stack_drop(stack, (int)i);
         if ((stack->unlock != NULL) && (stack->unlock() != 0))
                 return RAISE(&turtle_stack_clear, TURTLE_RETURN_UNLOCK_ERROR, STACK_C,
                     "could not release the lock");
@@ -771,8 +778,8 @@ static void stack_touch(struct turtle_stack * stack, int cell)
         stack->mru.insert(stack->mru.begin(), cell);
 }
 
-/* Load the tile of one grid cell; evicts beyond max_size unless tiles are pinned
- * by a residency plan (ref: stack.c:427-449). */
+/* Load the tile of one grid cell; the least recently used tiles are evicted beyond
+ * max_size (ref: stack.c:427-449). */
 static enum turtle_return stack_load_cell(struct turtle_stack * stack, int cell,
     turtle_function_t * caller)
 {
@@ -780,10 +787,8 @@ static enum turtle_return stack_load_cell(struct turtle_stack * stack, int cell,
         struct turtle_map * m;
         enum turtle_return rc = map_load_file(&m, stack->path[cell].c_str(), caller);
         if (rc != TURTLE_RETURN_SUCCESS) return rc;
-        if (stack->pinned == 0) {
-                while ((int)stack->mru.size() >= stack->max_size && !stack->mru.empty())
-                        stack_drop(stack, stack->mru.back());
-        }
+        while ((int)stack->mru.size() >= stack->max_size && !stack->mru.empty())
+                stack_drop(stack, stack->mru.back());
         m->stack = stack;
         stack->tile[cell] = m;
         stack->mru.insert(stack->mru.begin(), cell);
@@ -822,90 +827,88 @@ extern "C" enum turtle_return turtle_stack_load(struct turtle_stack * stack)
         return rc;
 }
 
-/* Scalar stack lookup with the ownership rules of tb::stack_elevation, loading
- * tiles on demand. Returns inside. */
+/* The tile that answers a query at (latitude, longitude), with the ownership rules of
+ * tb::stack_elevation, loading tiles on demand (and evicting beyond max_size, like the
+ * reference: stack.c:413-449). *owner = its cell, or -1. */
+static enum turtle_return stack_owner_scalar(struct turtle_stack * stack, double latitude,
+    double longitude, int * owner_, turtle_function_t * caller)
+{
+        *owner_ = -1;
+        if ((stack->latitude_n <= 0) || (stack->longitude_n <= 0) || isnan(latitude) ||
+            isnan(longitude))
+                return TURTLE_RETURN_SUCCESS;
+        /* the candidate cell and, by rounding at a tile edge, its neighbours */
+        double fx = (longitude - stack->longitude_0) / stack->longitude_delta;
+        double fy = (latitude - stack->latitude_0) / stack->latitude_delta;
+        if (!(fx >= 0.)) fx = 0.;
+        if (!(fy >= 0.)) fy = 0.;
+        const int cx = (fx < stack->longitude_n) ? (int)fx : stack->longitude_n - 1;
+        const int cy = (fy < stack->latitude_n) ? (int)fy : stack->latitude_n - 1;
+        int cells[9], n = 0;
+        cells[n++] = cy * stack->longitude_n + cx;
+        for (int jy = cy - 1; jy <= cy + 1; jy++)
+                for (int jx = cx - 1; jx <= cx + 1; jx++) {
+                        if ((jy < 0) || (jy >= stack->latitude_n) || (jx < 0) ||
+                            (jx >= stack->longitude_n) || ((jx == cx) && (jy == cy)))
+                                continue;
+                        cells[n++] = jy * stack->longitude_n + jx;
+                }
+        int owner = -1;
+        for (int k = 0; k < n; k++) {
+                const int cell = cells[k];
+                if (stack->path[cell].empty()) continue;
+                /* ownership only needs the tile meta (x0, y0, dx, nx ...): the header
+                 * read by turtle_stack_create when the tile is not loaded */
+                if (stack->tile[cell] == NULL) {
+                        if (!tb::tile_owns(stack->header[cell], latitude, longitude)) continue;
+                        enum turtle_return rc = stack_load_cell(stack, cell, caller);
+                        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+                } else if (!tb::tile_owns(map_desc(stack->tile[cell]), latitude, longitude))
+                        continue;
+                owner = cell;
+                break;
+        }
+        if ((owner < 0) && !((longitude < stack->longitude_0) ||
+                               (latitude < stack->latitude_0))) { /* ref: stack.c:413-425 */
+                const double qx = (longitude - stack->longitude_0) / stack->longitude_delta;
+                const double qy = (latitude - stack->latitude_0) / stack->latitude_delta;
+                if ((qx < stack->longitude_n) && (qy < stack->latitude_n)) {
+                        const int cell = (int)qy * stack->longitude_n + (int)qx;
+                        if (!stack->path[cell].empty()) {
+                                enum turtle_return rc = stack_load_cell(stack, cell, caller);
+                                if (rc != TURTLE_RETURN_SUCCESS) return rc;
+                                owner = cell;
+                        }
+                }
+        }
+        if (owner >= 0) stack_touch(stack, owner);
+        *owner_ = owner;
+        return TURTLE_RETURN_SUCCESS;
+}
+
+/* Scalar stack lookup (ref: turtle_stack_elevation, stack.c:338-361). */
 static enum turtle_return stack_elevation_scalar(struct turtle_stack * stack,
     double latitude, double longitude, double * elevation, int * inside,
     turtle_function_t * caller)
 {
-        int in = 0;
         if (inside != NULL) *inside = 0;
-        if ((stack->latitude_n > 0) && (stack->longitude_n > 0) && !isnan(latitude) &&
-            !isnan(longitude)) {
-                /* make the candidate cell and its neighbours resident, then apply
-                 * the device rule on this 3x3 window */
-                double fx = (longitude - stack->longitude_0) / stack->longitude_delta;
-                double fy = (latitude - stack->latitude_0) / stack->latitude_delta;
-                if (!(fx >= 0.)) fx = 0.;
-                if (!(fy >= 0.)) fy = 0.;
-                const int cx = (fx < stack->longitude_n) ? (int)fx : stack->longitude_n - 1;
-                const int cy = (fy < stack->latitude_n) ? (int)fy : stack->latitude_n - 1;
-                /* the exact owner is almost always the candidate cell */
-                int cells[9], n = 0;
-                cells[n++] = cy * stack->longitude_n + cx;
-                for (int jy = cy - 1; jy <= cy + 1; jy++)
-                        for (int jx = cx - 1; jx <= cx + 1; jx++) {
-                                if ((jy < 0) || (jy >= stack->latitude_n) || (jx < 0) ||
-                                    (jx >= stack->longitude_n) ||
-                                    ((jx == cx) && (jy == cy)))
-                                        continue;
-                                cells[n++] = jy * stack->longitude_n + jx;
-                        }
-                int owner = -1;
-                for (int k = 0; k < n; k++) {
-                        const int cell = cells[k];
-                        if (stack->path[cell].empty()) continue;
-                        /* ownership only needs the tile meta: x0, y0, dx, nx */
-                        if (stack->tile[cell] == NULL) {
-                                /* the header read by turtle_stack_create */
-                                if (!tb::tile_owns(stack->header[cell], latitude, longitude))
-                                        continue;
-                                enum turtle_return rc = stack_load_cell(stack, cell, caller);
-                                if (rc != TURTLE_RETURN_SUCCESS) {
-                                        *elevation = 0.;
-                                        return rc;
-                                }
-                        } else if (!tb::tile_owns(map_desc(stack->tile[cell]), latitude,
-                                       longitude))
-                                continue;
-                        owner = cell;
-                        break;
-                }
-                if (owner < 0) { /* ref: stack.c:413-425 */
-                        if (!((longitude < stack->longitude_0) ||
-                                (latitude < stack->latitude_0))) {
-                                const double qx = (longitude - stack->longitude_0) /
-                                    stack->longitude_delta;
-                                const double qy = (latitude - stack->latitude_0) /
-                                    stack->latitude_delta;
-                                if ((qx < stack->longitude_n) && (qy < stack->latitude_n)) {
-                                        const int cell =
-                                            (int)qy * stack->longitude_n + (int)qx;
-                                        if (!stack->path[cell].empty()) {
-                                                enum turtle_return rc =
-                                                    stack_load_cell(stack, cell, caller);
-                                                if (rc != TURTLE_RETURN_SUCCESS) {
-                                                        *elevation = 0.;
-                                                        return rc;
-                                                }
-                                                owner = cell;
-                                        }
-                                }
-                        }
-                }
-                if (owner >= 0) {
-                        stack_touch(stack, owner);
-                        in = tb::map_elevation(map_desc(stack->tile[owner]), longitude,
-                            latitude, *elevation);
-                        if (inside != NULL) {
-                                *inside = in;
-                                return TURTLE_RETURN_SUCCESS;
-                        }
-                        if (!in)
-                                return tbh::raise(caller, TURTLE_RETURN_DOMAIN_ERROR, MAP_C,
-                                    __LINE__, "point is outside of map");
+        int owner;
+        enum turtle_return rc = stack_owner_scalar(stack, latitude, longitude, &owner, caller);
+        if (rc != TURTLE_RETURN_SUCCESS) {
+                *elevation = 0.;
+                return rc;
+        }
+        if (owner >= 0) {
+                const int in = tb::map_elevation(map_desc(stack->tile[owner]), longitude,
+                    latitude, *elevation);
+                if (inside != NULL) {
+                        *inside = in;
                         return TURTLE_RETURN_SUCCESS;
                 }
+                if (!in)
+                        return tbh::raise(caller, TURTLE_RETURN_DOMAIN_ERROR, MAP_C, __LINE__,
+                            "point is outside of map");
+                return TURTLE_RETURN_SUCCESS;
         }
         *elevation = 0.; /* ref: stack.c:349-355 */
         if (inside != NULL) return TURTLE_RETURN_SUCCESS;
@@ -920,46 +923,20 @@ extern "C" enum turtle_return turtle_stack_elevation(struct turtle_stack * stack
             FN(&turtle_stack_elevation));
 }
 
-/* ref: turtle_stack_gradient, stack.c:364-388. Every tile is made resident first: the
- * answer is the one of the device rule tb::stack_gradient. */
+/* ref: turtle_stack_gradient, stack.c:364-388: the tile that answers an elevation query
+ * answers the gradient query (x = longitude, y = latitude). */
 extern "C" enum turtle_return turtle_stack_gradient(struct turtle_stack * stack,
     double latitude, double longitude, double * glat, double * glon, int * inside)
 {
         if (inside != NULL) *inside = 0;
-        enum turtle_return rc = tbh::stack_load_all(stack, FN(&turtle_stack_elevation));
+        int owner;
+        enum turtle_return rc = stack_owner_scalar(stack, latitude, longitude, &owner,
+            FN(&turtle_stack_elevation));
         if (rc != TURTLE_RETURN_SUCCESS) return rc;
-        tb::Geometry G;
-        memset(&G, 0x0, sizeof(G));
-        std::vector<tb::MapDesc> maps;
-        std::vector<tb::TileRec> tiles;
-        tb::StackDesc & S = G.stacks[0];
-        S.lat0 = stack->latitude_0;
-        S.dlat = stack->latitude_delta;
-        S.lon0 = stack->longitude_0;
-        S.dlon = stack->longitude_delta;
-        S.inv_dlat = (S.dlat > 0.) ? 1. / S.dlat : 0.;
-        S.inv_dlon = (S.dlon > 0.) ? 1. / S.dlon : 0.;
-        S.nlat = stack->latitude_n;
-        S.nlon = stack->longitude_n;
-        S.nlat_d = (double)S.nlat;
-        S.nlon_d = (double)S.nlon;
-        const tb::TileRec none = { NULL, 0., 0., -1, 0 };
-        for (size_t c = 0; c < stack->tile.size(); c++) {
-                if (stack->tile[c] == NULL) {
-                        tiles.push_back(none);
-                        continue;
-                }
-                const tb::TileRec rec = { stack->tile[c]->nodes.data(), stack->tile[c]->x0,
-                        stack->tile[c]->y0, (int)maps.size(), 0 };
-                tiles.push_back(rec);
-                maps.push_back(map_desc(stack->tile[c]));
-        }
         int in = 0;
-        if (!tiles.empty()) {
-                G.maps = maps.data();
-                G.tiles = tiles.data();
-                in = tb::stack_gradient(G, S, latitude, longitude, *glat, *glon);
-        }
+        if (owner >= 0)
+                in = tb::map_gradient(map_desc(stack->tile[owner]), longitude, latitude, *glon,
+                    *glat);
         if (!in) *glat = *glon = 0.;
         if (inside != NULL) {
                 *inside = in;
@@ -1045,6 +1022,7 @@ extern "C" enum turtle_return turtle_stepper_create(struct turtle_stepper ** ste
         s->state.last.elev0 = s->state.last.elev1 = 0.;
         s->state.last.lat = s->state.last.lon = s->state.last.alt = 0.;
         s->dirty = 1;
+        s->lookup_rc = TURTLE_RETURN_SUCCESS;
         memset(&s->flat.G, 0x0, sizeof(s->flat.G));
         stepper_reset_history(s);
         *stepper_ = s;
@@ -1053,17 +1031,10 @@ extern "C" enum turtle_return turtle_stepper_create(struct turtle_stepper ** ste
 
 static std::mutex g_residency_mutex;
 
-/* Drop the cached flattening (and the tile pins it holds) before any change. */
-static void stepper_invalidate(struct turtle_stepper * s)
-{
-        std::lock_guard<std::mutex> guard(g_residency_mutex);
-        if (!s->dirty)
-                for (size_t i = 0; i < s->data.size(); i++)
-                        if ((s->data[i].kind == tb::DATA_STACK) &&
-                            (s->data[i].stack->pinned > 0))
-                                s->data[i].stack->pinned--;
-        s->dirty = 1;
-}
+/* Drop the cached flattening before any change of the geometry. (The stepper holds no
+ * claim on the tiles of its stacks: the scalar calls resolve them on demand, see
+ * host_stack_lookup, so stacks and steppers may be destroyed in any order.) */
+static void stepper_invalidate(struct turtle_stepper * s) { s->dirty = 1; }
 
 extern "C" enum turtle_return turtle_stepper_destroy(struct turtle_stepper ** stepper)
 {
@@ -1246,7 +1217,8 @@ enum turtle_return tbh::stepper_flatten(struct turtle_stepper * s,
 
 /* Geodetic footprint of a projected map (tb::DataDesc::box): the border of the map is
  * walked node by node through the inverse projection; the box is widened by 1E-06 deg
- * (0.1 m) and dropped when the footprint wraps in longitude or is not finite. */
+ * (0.1 m) plus a bound on the bulge of an edge between two nodes, and dropped when the
+ * footprint wraps in longitude or is not finite. */
 static void map_geodetic_box(const struct turtle_map * m, const tb::ProjDesc & P, tb::DataDesc & d)
 {
         d.boxed = 0;
@@ -1269,7 +1241,16 @@ static void map_geodetic_box(const struct turtle_map * m, const tb::ProjDesc & P
                 }
         }
         if ((lo1 - lo0 > 90.) || (la1 > 89.) || (la0 < -89.)) return;
-        const double margin = 1E-06;
+        /* Between two border nodes h apart the extreme of latitude / longitude along the
+         * edge can exceed both nodes by at most h^2 / 8 x the second derivative along the
+         * edge, itself below 4 (1 + tan^2) / (R^2 cos) at the highest latitude of the
+         * footprint (a generous bound for a conformal projection of the ellipsoid): the
+         * box stays a superset of the footprint whatever the node spacing */
+        const double phi = std::max(fabs(la0), fabs(la1)) * M_PI / 180.;
+        const double h = std::max(fabs(m->dx), fabs(m->dy));
+        const double curvature = 4. * (1. + tan(phi) * tan(phi)) /
+            (TB_WGS84_B * TB_WGS84_B * cos(phi));
+        const double margin = 1E-06 + 0.125 * h * h * curvature * 180. / M_PI;
         d.box[0] = la0 - margin;
         d.box[1] = la1 + margin;
         d.box[2] = lo0 - margin;
@@ -1289,9 +1270,33 @@ static int tile_in_region(const tb::MapDesc & t, const struct turtle_residency *
         return 1;
 }
 
+/* The scalar calls resolve a stack query on the host like turtle_stack_elevation /
+ * turtle_client_elevation do: tiles are loaded ON DEMAND and evicted beyond the `size`
+ * given to turtle_stack_create (ref: stepper_step_stack / stepper_step_client,
+ * stepper.c:199-225; stack.c:413-449). A load error is kept for turtle_stepper_step to
+ * return. */
+static int host_stack_lookup(void * context, int stack_index, double latitude,
+    double longitude, double * z)
+{
+        struct turtle_stepper * s = (struct turtle_stepper *)context;
+        int k = 0;
+        for (size_t i = 0; i < s->data.size(); i++) {
+                if (s->data[i].kind != tb::DATA_STACK) continue;
+                if (k++ != stack_index) continue;
+                int inside = 0;
+                const enum turtle_return rc = (s->data[i].client != NULL) ?
+                    turtle_client_elevation(s->data[i].client, latitude, longitude, z, &inside) :
+                    turtle_stack_elevation(s->data[i].stack, latitude, longitude, z, &inside);
+                if ((rc != TURTLE_RETURN_SUCCESS) && (s->lookup_rc == TURTLE_RETURN_SUCCESS))
+                        s->lookup_rc = rc;
+                return (rc == TURTLE_RETURN_SUCCESS) ? inside : 0;
+        }
+        return 0;
+}
+
 /* Flatten the lists into tb::Geometry.
- *   load_tiles = 1: every tile of every stack is made resident on the HOST and the
- *                   descriptors point to host nodes (the scalar turtle.h calls);
+ *   load_tiles = 1: the flattening of the scalar turtle.h calls (host): maps point to
+ *                   host nodes, stacks are resolved through host_stack_lookup;
  *   load_tiles = 0: residency plan of a device -- tiles that are not on the host are
  *                   described from their file header only (F.src NULL, F.file set: the
  *                   freeze ingests them on the device), and tiles outside `region` are
@@ -1342,14 +1347,6 @@ enum turtle_return tbh::flatten_into(struct turtle_stepper * s, tb_flat_geometry
                         map_geodetic_box(d.map, G.transforms[d.transform], G.data[i]);
                 } else if (d.kind == tb::DATA_STACK) {
                         struct turtle_stack * st = d.stack;
-                        if (load_tiles) {
-                                st->pinned++;
-                                enum turtle_return rc = tbh::stack_load_all(st, caller);
-                                if (rc != TURTLE_RETURN_SUCCESS) {
-                                        st->pinned--;
-                                        return rc;
-                                }
-                        }
                         tb::StackDesc & S = G.stacks[G.n_stacks];
                         G.data[i].ref = G.n_stacks++;
                         S.lat0 = st->latitude_0;
@@ -1367,7 +1364,9 @@ enum turtle_return tbh::flatten_into(struct turtle_stepper * s, tb_flat_geometry
                         S.uniform = 1;
                         for (size_t c = 0; c < st->tile.size(); c++) {
                                 const struct turtle_map * t = st->tile[c];
-                                if ((t == NULL) && (load_tiles || st->path[c].empty())) {
+                                if (load_tiles || ((t == NULL) && st->path[c].empty())) {
+                                        /* (host flattening: stacks are resolved through
+                                         * G.host_stack, the tile table is not read) */
                                         F.tiles.push_back(none);
                                         continue;
                                 }
@@ -1453,6 +1452,8 @@ enum turtle_return tbh::flatten_into(struct turtle_stepper * s, tb_flat_geometry
         G.n_metas = first;
         G.maps = F.maps.data();
         G.tiles = F.tiles.data();
+        G.host_stack = load_tiles ? &host_stack_lookup : NULL;
+        G.host_context = load_tiles ? (void *)s : NULL;
         return TURTLE_RETURN_SUCCESS;
 }
 
@@ -1489,6 +1490,7 @@ extern "C" enum turtle_return turtle_stepper_step(struct turtle_stepper * steppe
         enum turtle_return rc = tbh::stepper_flatten(stepper, FN(&turtle_stepper_step));
         if (rc != TURTLE_RETURN_SUCCESS) return rc;
         const tb::Geometry & G = stepper->flat.G;
+        stepper->lookup_rc = TURTLE_RETURN_SUCCESS;
         double ds;
         if (G.range > 0.)
                 ds = tb::stepper_step<true>(G, stepper->lla, stepper->state, position,
@@ -1496,6 +1498,8 @@ extern "C" enum turtle_return turtle_stepper_step(struct turtle_stepper * steppe
         else
                 ds = tb::stepper_step<false>(G, stepper->lla, stepper->state, position,
                     direction);
+        if (stepper->lookup_rc != TURTLE_RETURN_SUCCESS)
+                return stepper->lookup_rc; /* raised by the stack / client call already */
         publish(stepper, latitude, longitude, altitude, elevation, index);
         if (step_length != NULL) *step_length = ds;
         if ((stepper->state.last.idx0 < 0) && (index == NULL))
@@ -1516,6 +1520,7 @@ extern "C" enum turtle_return turtle_stepper_position(struct turtle_stepper * st
         if (rc != TURTLE_RETURN_SUCCESS) return rc;
         const tb::Geometry & G = stepper->flat.G;
         const tb::LayerDesc layer = G.layers[layer_index];
+        stepper->lookup_rc = TURTLE_RETURN_SUCCESS;
         for (int k = 0; k < layer.n; k++) {
                 const tb::MetaDesc & meta = G.metas[layer.first + k];
                 const tb::DataDesc & d = G.data[meta.data];
@@ -1532,6 +1537,7 @@ extern "C" enum turtle_return turtle_stepper_position(struct turtle_stepper * st
                 } else {
                         inside = tb::map_elevation(G.maps[d.ref], longitude, latitude, z);
                 }
+                if (stepper->lookup_rc != TURTLE_RETURN_SUCCESS) return stepper->lookup_rc;
                 if (!inside) continue;
                 z += meta.offset;
                 if (G.geoid >= 0) { /* ref: stepper.c:905-914 */

@@ -60,7 +60,6 @@ struct turtle_stack {
         std::vector<tb::MapDesc> header;       /* per cell: shape and origin from the file
                                                 * header (no nodes), read once at creation */
         std::vector<int> mru;                  /* loaded cells, most recent first */
-        int pinned;                            /* > 0: residency plans hold the tiles */
 };
 
 /* ref: struct turtle_client, client.h:31-40 */
@@ -109,6 +108,7 @@ struct turtle_stepper {
         /* cached flattening */
         int dirty;
         tb_flat_geometry flat;
+        enum turtle_return lookup_rc; /* first tile-load error of the running scalar call */
 };
 
 namespace tbh {
@@ -121,7 +121,7 @@ enum turtle_return raise(turtle_function_t * fn, enum turtle_return rc,
 enum turtle_return stack_load_all(struct turtle_stack * stack,
     turtle_function_t * caller);
 
-/* (Re)build stepper->flat. Loads every tile of every stack. */
+/* (Re)build stepper->flat (host nodes; stacks resolved on demand). */
 enum turtle_return stepper_flatten(struct turtle_stepper * stepper,
     turtle_function_t * caller);
 /* Flatten into `F`, for the host (load_tiles) or for a device residency plan. */
