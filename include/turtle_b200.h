@@ -90,6 +90,8 @@ struct turtle_plan_counters {
         uint64_t samples;  /* geometry samples (stepper_sample equivalents) */
         uint64_t launches; /* CUDA kernels launched */
         double kernel_ms;  /* device time of the kernels (CUDA events), host-pointer calls only */
+        uint64_t rebuilds; /* local approximation: Jacobian columns evaluated (one ECEF ->
+                            * geodetic transform each, like a sample) */
 };
 
 /* ---- plans ---------------------------------------------------------------- */
@@ -183,6 +185,66 @@ TURTLE_API enum turtle_return turtle_stepper_trace_batch_device(
     const double * direction, const struct turtle_trace_rule * rule,
     struct turtle_trace_result * results, void * stream);
 
+/* ---- compact input / output of whole rays -----------------------------------------------
+ * turtle_stepper_trace_batch moves 48 bytes in and 96 bytes out per ray. The canonical
+ * caller needs neither: examples/example-stepper.c:102-140 (ref) shoots rays from ONE
+ * station, derives each direction from two angles (turtle_ecef_from_horizontal) and keeps
+ * ONE number per ray (the rock length). These entry points are that caller, batched.
+ *
+ * Fields: the columns of struct turtle_trace_result as separate arrays, any of them NULL
+ * (not wanted). position is [n][3], index is [n][2], the others are [n]. What a caller
+ * does not ask for is neither stored nor copied. */
+struct turtle_trace_fields {
+        double * length[TURTLE_TRACE_MEDIA];
+        double * total;
+        double * altitude;
+        double * position;
+        int32_t * n_steps;
+        int32_t * status;
+        int32_t * index;
+        uint32_t * medium_hash;
+        int32_t * n_changes;
+};
+/* A fan of n_azimuth x n_elevation rays from one origin. The direction of ray (i, j) is
+ * turtle_ecef_from_horizontal(latitude, longitude, azimuth[i], elevation[j]) TO THE BIT
+ * (ref: src/turtle/ecef.c:160-178): the sines and cosines of the n_azimuth + n_elevation
+ * angles are taken on the host, by the very calls of that function, and the device only
+ * multiplies and adds in its order. `azimuth` and `elevation` are HOST arrays, in degrees
+ * (also for the _device variant: they are the whole input of a call, a few kB).
+ * Ray order: ray r is (i, j) with
+ *     band = r / (n_azimuth * bundle), i = (r / bundle) % n_azimuth,
+ *     j = band * bundle + r % bundle,
+ * i.e. bands of `bundle` consecutive elevations, azimuth by azimuth within a band:
+ * bundle = 1 is elevation-major (r = j * n_azimuth + i), bundle = n_elevation is
+ * azimuth-major (r = i * n_elevation + j), bundle = 32 makes the 32 rays of a warp share
+ * one vertical plane. n_elevation must be a multiple of bundle (0 means 1). Listing the
+ * lowest elevations first starts the longest rays first. */
+struct turtle_fan {
+        double latitude, longitude; /* the station: local frame of azimuth / elevation */
+        double position[3];         /* ECEF origin of every ray (turtle_stepper_position) */
+        size_t n_azimuth, n_elevation;
+        const double * azimuth;
+        const double * elevation;
+        size_t bundle;
+};
+/* Trace the fan. `results` (n records) and `fields` may each be NULL; both are HOST memory
+ * here and DEVICE memory in the _device variant. */
+TURTLE_API enum turtle_return turtle_stepper_trace_fan(struct turtle_plan * plan,
+    const struct turtle_fan * fan, const struct turtle_trace_rule * rule,
+    struct turtle_trace_result * results, const struct turtle_trace_fields * fields);
+TURTLE_API enum turtle_return turtle_stepper_trace_fan_device(struct turtle_plan * plan,
+    const struct turtle_fan * fan, const struct turtle_trace_rule * rule,
+    struct turtle_trace_result * results, const struct turtle_trace_fields * fields,
+    void * stream);
+/* turtle_stepper_trace_batch with field arrays instead of records. */
+TURTLE_API enum turtle_return turtle_stepper_trace_fields(struct turtle_plan * plan, size_t n,
+    const double * position, const double * direction, const struct turtle_trace_rule * rule,
+    const struct turtle_trace_fields * fields);
+TURTLE_API enum turtle_return turtle_stepper_trace_fields_device(struct turtle_plan * plan,
+    size_t n, const double * position, const double * direction,
+    const struct turtle_trace_rule * rule, const struct turtle_trace_fields * fields,
+    void * stream);
+
 /* ---- the stream of medium changes along every ray --------
  * What a Monte-Carlo engine integrates over the steps -- column density, energy loss per
  * medium, entry and exit points of the rock -- needs more than the per-medium totals of
@@ -215,6 +277,10 @@ TURTLE_API enum turtle_return turtle_states_create(
     struct turtle_plan * plan, size_t n, struct turtle_states ** states);
 TURTLE_API void turtle_states_destroy(struct turtle_states ** states);
 TURTLE_API enum turtle_return turtle_states_reset(struct turtle_states * states);
+/* Bytes of HBM held per particle: the last sample (9 doubles), the stale-Jacobian mask and,
+ * when the plan's range is > 0, the local approximations of the transforms the geometry
+ * uses (15 doubles for a geodetic stack, 25 for a projected map over a stack ...). */
+TURTLE_API size_t turtle_states_bytes_per_particle(const struct turtle_states * states);
 TURTLE_API enum turtle_return turtle_stepper_step_batch(
     struct turtle_plan * plan, struct turtle_states * states, size_t n,
     double * position, const double * direction, double * latitude,
@@ -318,6 +384,13 @@ TURTLE_API int turtle_b200_device_count(void);
  * dependent-chain DFMA micro-benchmark kernel; used as the compute roofline. */
 TURTLE_API double turtle_b200_dfma_peak(int repeats);
 TURTLE_API const char * turtle_b200_version(void);
+/* Registers per thread and static shared memory of a built kernel, by role: "trace_stack",
+ * "trace", "trace_proj", "trace_lla", "trace_lla_proj", "trace_stack_stream", "walk",
+ * "walk_proj", "walk_lla", "walk_lla_proj", "to_geodetic", "map_elevation",
+ * "map_elevation_ecef". Returns 0, -1 for an unknown role, -2 without a device. The
+ * measurement tools use it to check that a committed profile (profiles/) still describes
+ * the kernel they are timing. */
+TURTLE_API int turtle_b200_kernel_info(const char * name, int * registers, int * shared_bytes);
 /* Device self test of the shared-reciprocal division used by the kernels against the
  * compiler's IEEE division on 2 * n random operand pairs: number of results that
  * differ in any bit (0 expected), -1 without a device. */

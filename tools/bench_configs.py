@@ -29,7 +29,8 @@ import torch  # noqa: E402
 import bench as B  # noqa: E402
 import turtle_b200 as tb  # noqa: E402
 from oracle import harness as H  # noqa: E402
-from tests.common import Scene, compare_traces  # noqa: E402
+from oracle import parity as P  # noqa: E402
+from tests.common import Scene  # noqa: E402
 from turtle_b200 import synth  # noqa: E402
 
 DEV = "cuda:0"
@@ -55,15 +56,31 @@ def trace_config(name, scene, pos, dirs, rule_o, rule_g, args, ops_per_sample, n
     n = len(pos)
     d_pos, d_dir = torch.from_numpy(pos).to(DEV), torch.from_numpy(dirs).to(DEV)
     d_res = torch.empty((n, 96), dtype=torch.uint8, device=DEV)
-    ms = timed(lambda: plan.trace_device(n, d_pos, d_dir, rule_g, d_res), args.steps)
+    if args.max_steps:  # profiling: bound the lone-lane tail of the launch
+        rule_g = tb.trace_rule(rule_g.altitude_max, length_max=rule_g.length_max,
+                               max_steps=args.max_steps)
+        rule_o = H.rule(rule_o.altitude_max, length_max=rule_o.length_max,
+                        max_steps=args.max_steps)
+    ms = timed(lambda: plan.trace_device(n, d_pos, d_dir, rule_g, d_res), args.steps, args.warmup)
     c = plan.counters(sync=True)
+    if args.no_cpu:
+        print(json.dumps({"config": name, "rays": n, "ms_per_step": ms, "Mrays_per_s": n / ms / 1e3,
+                          "samples": c["samples"], "steps": c["steps"], "rebuilds": c["rebuilds"],
+                          "Gsamples_per_s": c["samples"] / ms / 1e6}), flush=True)
+        return
     got = d_res.cpu().numpy().view(tb.TRACE_RESULT).reshape(n)
     # reference on all cores, strided sample
     stride = max(1, n // args.cpu_rays)
     ora = scene.oracle(locked=True)
     want, steps, seconds = ora.trace(pos[::stride], dirs[::stride], rule_o,
                                      threads=os.cpu_count())
-    rep = compare_traces(want, got[::stride])
+    rep = P.report(want, got[::stride])
+    floor = None
+    if H.available(H.REF_FMA) and H.best_oracle() == H.REF:
+        fma, _, _ = scene.oracle(library=H.REF_FMA, locked=True).trace(
+            pos[::stride], dirs[::stride], rule_o, threads=os.cpu_count())
+        floor = P.report(want, fma)
+    sys.stderr.write(P.table(rep, floor) + "\n")
     dfma = tb.dfma_peak(3)
     achieved = ops_per_sample * c["samples"] / (ms * 1e-3) / 1e12
     line = {
@@ -77,7 +94,10 @@ def trace_config(name, scene, pos, dirs, rule_o, rule_g, args, ops_per_sample, n
                          "ns_per_step": 1e9 * seconds / max(steps, 1), "kind": "reference"
                          if H.best_oracle() == H.REF else "port",
                          "sample": "every %d-th ray (%d rays)" % (stride, len(want))},
-        "parity": rep, "status_counts": np.bincount(got["status"], minlength=5).tolist(),
+        "rebuilds_per_sample": c.get("rebuilds", 0) / max(c["samples"], 1),
+        "parity": rep, "noise_floor": floor,
+        "parity_vs_floor": P.against_floor(rep, floor) if floor else None,
+        "status_counts": np.bincount(got["status"], minlength=5).tolist(),
         "plan_bytes": plan.bytes,
     }
     line["speedup_vs_cpu"] = line["Mrays_per_s"] / line["cpu_baseline"]["Mrays_per_s"]
@@ -167,6 +187,7 @@ def c4(args):
     d_alt = torch.empty(n, dtype=torch.float64, device=DEV)
     d_idx = torch.empty((n, 2), dtype=torch.int32, device=DEV)
     total_ms, sample_dirs, got_step, got_alt, got_idx = 0., [], [], [], []
+    rebuilds = 0
     for rep in range(2):  # pass 0 = warm-up, pass 1 = timed
         states.reset()
         d_pos = d_pos0.clone()
@@ -182,11 +203,17 @@ def c4(args):
             e1.record()
             torch.cuda.synchronize()
             total_ms += e0.elapsed_time(e1)
-            if rep == 1:
+            rebuilds += plan.counters(sync=True)["rebuilds"] if rep == 1 else 0
+            if rep == 1 and not args.no_cpu:
                 sample_dirs.append(d_dir[::stride].cpu().numpy())
                 got_step.append(d_step[::stride].cpu().numpy())
                 got_alt.append(d_alt[::stride].cpu().numpy())
                 got_idx.append(d_idx[::stride].cpu().numpy())
+    if args.no_cpu:
+        print(json.dumps({"config": "c4", "particles": n, "walk_steps": k, "ms_total": total_ms,
+                          "Msteps_per_s": n * k / total_ms / 1e3,
+                          "rebuilds_per_step": rebuilds / (n * k)}), flush=True)
+        return
     ora = scene.oracle(locked=True)
     want = ora.walk(origin[::stride], np.stack(sample_dirs), threads=os.cpu_count())
     gs, ga, gi = np.stack(got_step), np.stack(got_alt), np.stack(got_idx)
@@ -199,7 +226,8 @@ def c4(args):
         "per-particle stepper state on the device" % (n, k, scene.range),
         "particles": n, "walk_steps": k, "ms_total": total_ms,
         "Msteps_per_s": n * k / total_ms / 1e3, "ns_per_step": total_ms * 1e6 / (n * k),
-        "state_bytes_per_particle": 8 * 9 + 224 * 2,
+        "state_bytes_per_particle": int(states.bytes_per_particle),
+        "rebuilds_per_step": rebuilds / (n * k),
         "cpu_baseline": {"Msteps_per_s": m * k / want["seconds"] / 1e6, "cores": os.cpu_count(),
                          "ns_per_step": 1e9 * want["seconds"] / (m * k),
                          "sample": "every %d-th particle (%d particles)" % (stride, m)},
@@ -252,12 +280,17 @@ def c5(args):
     d_in = torch.zeros(n, dtype=torch.int32, device=DEV)
     P = lambda t: t.data_ptr()  # noqa: E731
     ms_geo = timed(lambda: tb.api._check(lib.turtle_ecef_to_geodetic_batch_device(
-        n, P(d_ecef), P(d_lat), P(d_lon), P(d_alt), None)), args.steps)
+        n, P(d_ecef), P(d_lat), P(d_lon), P(d_alt), None)), args.steps, args.warmup)
     ms_map = timed(lambda: tb.api._check(lib.turtle_map_elevation_batch_device(
-        mp.handle, n, P(d_lon), P(d_lat), P(d_z), P(d_in), None)), args.steps)
+        mp.handle, n, P(d_lon), P(d_lat), P(d_z), P(d_in), None)), args.steps, args.warmup)
     z_two = d_z[::4096].cpu().numpy().copy()
     ms_fused = timed(lambda: tb.api._check(lib.turtle_map_elevation_ecef_batch_device(
-        mp.handle, n, P(d_ecef), P(d_lat), P(d_lon), P(d_alt), P(d_z), P(d_in), None)), args.steps)
+        mp.handle, n, P(d_ecef), P(d_lat), P(d_lon), P(d_alt), P(d_z), P(d_in), None)), args.steps,
+        args.warmup)
+    if args.no_cpu:
+        print(json.dumps({"config": "c5", "points": n, "ms_to_geodetic": ms_geo,
+                          "ms_map_elevation": ms_map, "ms_fused": ms_fused}), flush=True)
+        return
     # oracle on a strided sample
     stride = max(1, n // args.cpu_rays)
     ecef_s = d_ecef[::stride].cpu().numpy()
@@ -316,6 +349,10 @@ def main():
     ap.add_argument("--cpu-rays", type=int, default=1 << 18)
     ap.add_argument("--map-nodes", type=int, default=20000)
     ap.add_argument("--schedule", type=int, default=0)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--max-steps", type=int, default=0,
+                    help="profiling: stop rays after this many steps (bounds the launch tail)")
+    ap.add_argument("--no-cpu", action="store_true", help="GPU part only (ncu captures)")
     args = ap.parse_args()
     if args.config == "c1" and args.range is None:
         args.range = 0.

@@ -43,11 +43,27 @@ class ResidencyReport(C.Structure):
                 ("read_ms", C.c_double), ("upload_ms", C.c_double)]
 
 
+class TraceFields(C.Structure):
+    """struct turtle_trace_fields (include/turtle_b200.h): one array per column, NULL = not
+    wanted."""
+    _fields_ = [("length", C.c_void_p * 4), ("total", C.c_void_p), ("altitude", C.c_void_p),
+                ("position", C.c_void_p), ("n_steps", C.c_void_p), ("status", C.c_void_p),
+                ("index", C.c_void_p), ("medium_hash", C.c_void_p), ("n_changes", C.c_void_p)]
+
+
+class Fan(C.Structure):
+    """struct turtle_fan (include/turtle_b200.h)."""
+    _fields_ = [("latitude", C.c_double), ("longitude", C.c_double),
+                ("position", C.c_double * 3), ("n_azimuth", C.c_size_t),
+                ("n_elevation", C.c_size_t), ("azimuth", C.c_void_p),
+                ("elevation", C.c_void_p), ("bundle", C.c_size_t)]
+
+
 class PlanCounters(C.Structure):
     """struct turtle_plan_counters (include/turtle_b200.h)."""
     _fields_ = [("rays", C.c_uint64), ("steps", C.c_uint64),
                 ("samples", C.c_uint64), ("launches", C.c_uint64),
-                ("kernel_ms", C.c_double)]
+                ("kernel_ms", C.c_double), ("rebuilds", C.c_uint64)]
 
 
 ERROR_HANDLER = C.CFUNCTYPE(None, C.c_int, C.c_void_p, C.c_char_p)
@@ -143,6 +159,14 @@ SIGNATURES = {
     # rays
     "turtle_stepper_trace_batch": (_I, [_P, _N, _P, _P, C.POINTER(TraceRule), _P]),
     "turtle_stepper_trace_batch_device": (_I, [_P, _N, _P, _P, C.POINTER(TraceRule), _P, _P]),
+    "turtle_stepper_trace_fan": (_I, [_P, C.POINTER(Fan), C.POINTER(TraceRule), _P,
+                                      C.POINTER(TraceFields)]),
+    "turtle_stepper_trace_fan_device": (_I, [_P, C.POINTER(Fan), C.POINTER(TraceRule), _P,
+                                             C.POINTER(TraceFields), _P]),
+    "turtle_stepper_trace_fields": (_I, [_P, _N, _P, _P, C.POINTER(TraceRule),
+                                         C.POINTER(TraceFields)]),
+    "turtle_stepper_trace_fields_device": (_I, [_P, _N, _P, _P, C.POINTER(TraceRule),
+                                                C.POINTER(TraceFields), _P]),
     "turtle_stepper_trace_crossings": (_I, [_P, _N, _P, _P, C.POINTER(TraceRule), _P, _P, _I]),
     "turtle_stepper_trace_crossings_device": (_I, [_P, _N, _P, _P, C.POINTER(TraceRule), _P, _P,
                                                    _I, _P]),
@@ -150,6 +174,7 @@ SIGNATURES = {
     "turtle_states_create": (_I, [_P, _N, _PP]),
     "turtle_states_destroy": (None, [_PP]),
     "turtle_states_reset": (_I, [_P]),
+    "turtle_states_bytes_per_particle": (_N, [_P]),
     "turtle_stepper_step_batch": (_I, [_P, _P, _N] + [_P] * 8),
     "turtle_stepper_step_batch_device": (_I, [_P, _P, _N] + [_P] * 8 + [_P]),
     "turtle_stepper_position_batch": (_I, [_P, _N, _P, _P, _P, _I, _P, _P]),
@@ -177,6 +202,7 @@ SIGNATURES = {
     "turtle_b200_device_count": (_I, []),
     "turtle_b200_dfma_peak": (_D, [_I]),
     "turtle_b200_version": (C.c_char_p, []),
+    "turtle_b200_kernel_info": (_I, [C.c_char_p, c_int_p, c_int_p]),
     "turtle_b200_selftest_division": (C.c_longlong, [_N, C.c_uint64]),
 }
 

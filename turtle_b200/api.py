@@ -9,7 +9,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import (ERROR_HANDLER, MapInfo, PlanCounters, Residency, ResidencyReport, TraceRule,
+from ._lib import (ERROR_HANDLER, Fan, MapInfo, PlanCounters, TraceFields, Residency, ResidencyReport, TraceRule,
                    lib)
 
 TRACE_RESULT = np.dtype([
@@ -77,6 +77,14 @@ def _ptr(a):
 
 def device_count():
     return lib.turtle_b200_device_count()
+
+
+def kernel_info(role):
+    """(registers per thread, static shared bytes) of a built kernel, or None."""
+    r, sh = C.c_int(), C.c_int()
+    if lib.turtle_b200_kernel_info(role.encode(), C.byref(r), C.byref(sh)) != 0:
+        return None
+    return r.value, sh.value
 
 
 def dfma_peak(repeats=3):
@@ -407,7 +415,7 @@ class Plan:
         c = PlanCounters()
         lib.turtle_plan_counters_get(self._p, C.byref(c))
         return dict(rays=c.rays, steps=c.steps, samples=c.samples, launches=c.launches,
-                    kernel_ms=c.kernel_ms)
+                    kernel_ms=c.kernel_ms, rebuilds=c.rebuilds)
 
     def trace(self, position, direction, rule, results=None):
         """Host arrays in, host records out (turtle_stepper_trace_batch)."""
@@ -430,6 +438,65 @@ class Plan:
             self._p, n, _ptr(position), _ptr(direction), C.byref(rule), _ptr(results),
             _ptr(crossings), max_crossings))
         return results, crossings
+
+    # ---- compact input / output (turtle_stepper_trace_fan / _fields) ---------------------
+    FIELD_DTYPES = dict(length0="<f8", length1="<f8", length2="<f8", length3="<f8", total="<f8",
+                        altitude="<f8", position="<f8", n_steps="<i4", status="<i4",
+                        index="<i4", medium_hash="<u4", n_changes="<i4")
+
+    @classmethod
+    def host_fields(cls, n, names):
+        """Host arrays for the named columns of a trace result -> dict name -> array."""
+        shape = dict(position=(n, 3), index=(n, 2))
+        return {k: np.zeros(shape.get(k, (n,)), dtype=cls.FIELD_DTYPES[k]) for k in names}
+
+    @staticmethod
+    def _fields_struct(arrays):
+        """dict name -> array (numpy) or tensor (torch, device) -> struct turtle_trace_fields"""
+        f = TraceFields()
+        for k, a in arrays.items():
+            p = _ptr(a).value
+            if k.startswith("length"):
+                f.length[int(k[-1])] = p
+            else:
+                setattr(f, k, p)
+        return f
+
+    @staticmethod
+    def make_fan(latitude, longitude, position, azimuth, elevation, bundle=1):
+        """struct turtle_fan over host arrays of angles (kept alive by the returned pair)."""
+        az, el = _f8(azimuth), _f8(elevation)
+        fan = Fan(latitude, longitude, (C.c_double * 3)(*[float(x) for x in position]),
+                  len(az), len(el), _ptr(az), _ptr(el), bundle)
+        return fan, (az, el)
+
+    def trace_fan(self, fan, rule, results=None, fields=None):
+        """turtle_stepper_trace_fan: host records and / or host field arrays out."""
+        f = self._fields_struct(fields) if fields else None
+        _check(lib.turtle_stepper_trace_fan(
+            self._p, C.byref(fan[0]), C.byref(rule), _ptr(results) if results is not None else None,
+            C.byref(f) if f is not None else None))
+        return results, fields
+
+    def trace_fan_device(self, fan, rule, results=None, fields=None, stream=None):
+        f = self._fields_struct(fields) if fields else None
+        _check(lib.turtle_stepper_trace_fan_device(
+            self._p, C.byref(fan[0]), C.byref(rule), _ptr(results) if results is not None else None,
+            C.byref(f) if f is not None else None, C.c_void_p(stream) if stream else None))
+
+    def trace_fields(self, position, direction, rule, fields):
+        """turtle_stepper_trace_fields: host rays in, host field arrays out."""
+        position, direction = _f8(position, (-1, 3)), _f8(direction, (-1, 3))
+        f = self._fields_struct(fields)
+        _check(lib.turtle_stepper_trace_fields(self._p, len(position), _ptr(position),
+                                               _ptr(direction), C.byref(rule), C.byref(f)))
+        return fields
+
+    def trace_fields_device(self, n, position, direction, rule, fields, stream=None):
+        f = self._fields_struct(fields)
+        _check(lib.turtle_stepper_trace_fields_device(
+            self._p, n, _ptr(position), _ptr(direction), C.byref(rule), C.byref(f),
+            C.c_void_p(stream) if stream else None))
 
     def trace_device(self, n, position, direction, rule, results, stream=None):
         """Device tensors in / out (turtle_stepper_trace_batch_device), asynchronous."""
@@ -490,6 +557,10 @@ class States:
 
     def reset(self):
         _check(lib.turtle_states_reset(self._p))
+
+    @property
+    def bytes_per_particle(self):
+        return lib.turtle_states_bytes_per_particle(self._p)
 
     def __del__(self):
         if getattr(self, "_p", None):

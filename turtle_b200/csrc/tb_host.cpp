@@ -1005,7 +1005,10 @@ static const char * STEPPER_C = "src/turtle/stepper.c";
 
 static void stepper_reset_history(struct turtle_stepper * stepper)
 {
-        tb::state_reset(stepper->state, stepper->lla, tb::MAX_TRANSFORMS);
+        tb::state_reset(stepper->state);
+        /* every reference point (and the rest of the state, never read before it is
+         * written) at DBL_MAX: stepper.c:602-615 */
+        for (int i = 0; i < tb::LLA_ROWS_MAX; i++) stepper->lla[i] = DBL_MAX;
 }
 
 extern "C" enum turtle_return turtle_stepper_create(struct turtle_stepper ** stepper_)
@@ -1129,9 +1132,8 @@ static int stepper_transform(struct turtle_stepper * stepper, const char * name,
         tbh::projection_to_desc(projection, &t.proj);
         stepper->transforms.push_back(t);
         const int i = (int)stepper->transforms.size() - 1;
-        if (i < tb::MAX_TRANSFORMS)
-                stepper->lla[i].ref_ecef[0] = stepper->lla[i].ref_ecef[1] =
-                    stepper->lla[i].ref_ecef[2] = DBL_MAX; /* stepper.c:349-351 */
+        if (i < tb::MAX_TRANSFORMS) /* stepper.c:349-351 (host blocks: LLA_BLOCK_MAX rows) */
+                for (int k = 0; k < 3; k++) stepper->lla[tb::LLA_BLOCK_MAX * i + k] = DBL_MAX;
         return i;
 }
 
@@ -1452,8 +1454,39 @@ enum turtle_return tbh::flatten_into(struct turtle_stepper * s, tb_flat_geometry
         G.n_metas = first;
         G.maps = F.maps.data();
         G.tiles = F.tiles.data();
+        /* per projected transform: the union of the footprints of its maps, widened by what
+         * the local approximation can be off in latitude / longitude within its range */
+        for (int t = 0; t < tb::MAX_TRANSFORMS; t++) {
+                G.tboxed[t] = 0;
+                G.tbox[t][0] = G.tbox[t][2] = DBL_MAX;
+                G.tbox[t][1] = G.tbox[t][3] = -DBL_MAX;
+        }
+        for (int t = 0; t < G.n_transforms; t++) {
+                if (G.transforms[t].type == tb::PROJ_GEODETIC) continue;
+                int all = 1, any = 0;
+                for (int i = 0; i < G.n_data; i++) {
+                        if ((G.data[i].kind != tb::DATA_MAP) || (G.data[i].transform != t)) continue;
+                        any = 1;
+                        if (!G.data[i].boxed) all = 0;
+                        G.tbox[t][0] = std::min(G.tbox[t][0], G.data[i].box[0]);
+                        G.tbox[t][1] = std::max(G.tbox[t][1], G.data[i].box[1]);
+                        G.tbox[t][2] = std::min(G.tbox[t][2], G.data[i].box[2]);
+                        G.tbox[t][3] = std::max(G.tbox[t][3], G.data[i].box[3]);
+                }
+                /* (a sample in range is within r sqrt 3 of its reference point) */
+                const double r = (G.range > 0.) ? G.range : 0.;
+                const double slack = 4. * (r * r / TB_WGS84_B + 2. * r + 1E-03) / TB_WGS84_B * 180. /
+                    M_PI / std::max(0.02,
+                        cos(std::max(fabs(G.tbox[t][0]), fabs(G.tbox[t][1])) * M_PI / 180.));
+                G.tboxed[t] = any && all && isfinite(slack);
+                G.tbox[t][0] -= slack;
+                G.tbox[t][1] += slack;
+                G.tbox[t][2] -= slack;
+                G.tbox[t][3] += slack;
+        }
         G.host_stack = load_tiles ? &host_stack_lookup : NULL;
         G.host_context = load_tiles ? (void *)s : NULL;
+        tb::lla_layout(G, load_tiles);
         return TURTLE_RETURN_SUCCESS;
 }
 
@@ -1492,12 +1525,11 @@ extern "C" enum turtle_return turtle_stepper_step(struct turtle_stepper * steppe
         const tb::Geometry & G = stepper->flat.G;
         stepper->lookup_rc = TURTLE_RETURN_SUCCESS;
         double ds;
+        const tb::LlaView V = { stepper->lla, 1 };
         if (G.range > 0.)
-                ds = tb::stepper_step<true>(G, stepper->lla, stepper->state, position,
-                    direction);
+                ds = tb::stepper_step<true>(G, V, stepper->state, position, direction);
         else
-                ds = tb::stepper_step<false>(G, stepper->lla, stepper->state, position,
-                    direction);
+                ds = tb::stepper_step<false>(G, V, stepper->state, position, direction);
         if (stepper->lookup_rc != TURTLE_RETURN_SUCCESS)
                 return stepper->lookup_rc; /* raised by the stack / client call already */
         publish(stepper, latitude, longitude, altitude, elevation, index);

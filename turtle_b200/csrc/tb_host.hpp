@@ -104,7 +104,7 @@ struct turtle_stepper {
         double local_range, slope_factor, resolution_factor;
         /* last sample (stepper.h:93-98) and local approximations (stepper.h:45-58) */
         tb::StepperState state;
-        tb::LlaState lla[tb::MAX_TRANSFORMS];
+        double lla[tb::LLA_ROWS_MAX]; /* tb::LlaView of stride 1, blocks of LLA_BLOCK_MAX */
         /* cached flattening */
         int dirty;
         tb_flat_geometry flat;

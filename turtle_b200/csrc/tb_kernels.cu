@@ -57,8 +57,8 @@ static const char * BATCH_CU = "turtle_b200/csrc/tb_kernels.cu";
 
 namespace {
 
-enum { MODE_IDLE = 0, MODE_INIT = 1, MODE_TENT = 2, MODE_BISECT = 3, MODE_REBUILD = 4,
-       MODE_FINISH = 5,
+enum { MODE_IDLE = 0, MODE_INIT = 1, MODE_TENT = 2, MODE_BISECT = 3,
+       MODE_REBUILD = 4, /* runs the three transforms of a stale Jacobian that is about to be read */
        MODE_WAIT = 6, /* holds a queue ticket whose ray has not arrived on the device yet */
        MODE_DONE = 7  /* trace: the record is complete in shared memory, to be written out */ };
 
@@ -81,6 +81,17 @@ struct TraceArgs {
         /* medium changes of every ray (turtle_stepper_trace_crossings), or NULL */
         turtle_trace_crossing * crossings;
         int max_crossings;
+        /* fan input (turtle_stepper_trace_fan; position == NULL): every ray starts at
+         * fan_origin; direction of ray (i, j) from the host's sines / cosines of the
+         * angles, fan_az[i] = { sin az, cos az }, fan_el[j] = { cos el, sin el }, and the
+         * local East / North / Up vectors (ecef.c:136-178) */
+        const double2 * fan_az;
+        const double2 * fan_el;
+        double fan_origin[3], fan_e[3], fan_n[3], fan_u[3];
+        unsigned long long fan_naz, fan_bundle, fan_ray0; /* ray0: first ray of this launch */
+        /* field outputs (turtle_trace_fields: device arrays, any NULL), when use_fields */
+        turtle_trace_fields fields;
+        int use_fields;
 };
 
 #define STREAM_ABORT (~0ull)
@@ -141,7 +152,9 @@ enum { F_POS = 0, F_DIR = 3, F_ALT = 6, F_ELEV0, F_ELEV1, F_DS, F_DS0, F_DS1,
        N_F = F_LON + 1 };
 enum { I_IDX0 = 0, I_IDX1, I_MEDIUM0, I_NSTEPS, I_NCHANGES, I_HASH, I_RAYLO, I_RAYHI,
        N_I_BASE,
-       I_PEND = N_I_BASE, I_PEND_N0, I_RESUME, I_RB_AXIS, N_I };
+       I_PEND = N_I_BASE, /* + local approximation: transforms whose Jacobian is stale */
+       I_RB_MASK,         /*   ... of which the ones being rebuilt now (MODE_REBUILD) */
+       I_RESUME, I_RB_AXIS, N_I };
 
 /* Only the rows a kernel uses are allocated: the shared memory a CTA does not take is
  * L1 cache for the DEM gathers (17 + 4 kB per CTA for a trace without the local
@@ -170,13 +183,19 @@ __global__ void __launch_bounds__(128, MINB)
 #define SI(k) store.i[((k) < NI) ? (k) : 0][tid]
 
         int mode = MODE_IDLE;
-        tb::LlaState lla[LLA ? tb::MAX_TRANSFORMS : 1];
-        unsigned my_steps = 0u, my_samples = 0u;
+        /* local approximation: G.lla_rows columns of per-lane state in DYNAMIC shared memory
+         * (sized by the transforms the geometry uses, tb::LlaView) */
+        extern __shared__ double lla_store[];
+        const tb::LlaView V = { lla_store + tid, 128 };
+        unsigned my_steps = 0u, my_samples = 0u, my_rebuilds = 0u;
+        constexpr bool LLA_COUNT = LLA;
         bool exhausted = false;
         bool pending_wait = false; /* warp uniform: some lane holds a ticket */
         int owed = -1;             /* chunk whose completion count this lane still owes */
         unsigned iteration = 0u;
-        const unsigned long long t_start = STREAM ? global_ns() : 0ull;
+        unsigned long long t_wait = 0ull; /* STREAM: when this lane took its ticket */
+        int hold = 0; /* LLA, warp uniform: light iterations since the last heavy one */
+        constexpr int LIGHT_MIN = 5, HOLD_MAX = 24;
 
         for (;;) {
                 if (STREAM && ((++iteration & 127u) == 0u)) settle_done(A, owed);
@@ -187,6 +206,31 @@ __global__ void __launch_bounds__(128, MINB)
                  * the stores into a PEER's memory (multi-GPU) cheap
                  * on NVLink, where every request is a packet. */
                 unsigned done_mask = __ballot_sync(FULL, mode == MODE_DONE);
+                if ((done_mask != 0u) && A.use_fields && (mode == MODE_DONE)) {
+                        /* field arrays: the lane stores what the caller asked for itself */
+                        const unsigned long long ray =
+                            ((unsigned long long)(unsigned)SI(I_RAYHI) << 32) |
+                            (unsigned long long)(unsigned)SI(I_RAYLO);
+#pragma unroll
+                        for (int m = 0; m < TURTLE_TRACE_MEDIA; m++)
+                                if (A.fields.length[m] != NULL) A.fields.length[m][ray] = SF(F_LEN + m);
+                        if (A.fields.total != NULL) A.fields.total[ray] = SF(F_TOTAL);
+                        if (A.fields.altitude != NULL) A.fields.altitude[ray] = SF(F_ALT);
+                        if (A.fields.position != NULL) {
+                                A.fields.position[3 * ray] = SF(F_POS);
+                                A.fields.position[3 * ray + 1] = SF(F_POS + 1);
+                                A.fields.position[3 * ray + 2] = SF(F_POS + 2);
+                        }
+                        if (A.fields.n_steps != NULL) A.fields.n_steps[ray] = SI(I_NSTEPS);
+                        if (A.fields.status != NULL) A.fields.status[ray] = SI(I_MEDIUM0);
+                        if (A.fields.index != NULL) {
+                                A.fields.index[2 * ray] = SI(I_IDX0);
+                                A.fields.index[2 * ray + 1] = SI(I_IDX1);
+                        }
+                        if (A.fields.medium_hash != NULL)
+                                A.fields.medium_hash[ray] = (uint32_t)SI(I_HASH);
+                        if (A.fields.n_changes != NULL) A.fields.n_changes[ray] = SI(I_NCHANGES);
+                }
                 if (done_mask != 0u) __syncwarp(); /* the records are read across lanes */
                 const bool wrote = done_mask != 0u;
                 while (done_mask != 0u) {
@@ -196,7 +240,7 @@ __global__ void __launch_bounds__(128, MINB)
                         const unsigned long long ray =
                             ((unsigned long long)(unsigned)store.i[I_RAYHI][t] << 32) |
                             (unsigned long long)(unsigned)store.i[I_RAYLO][t];
-                        if (lane < 12u) {
+                        if ((lane < 12u) && (A.results != NULL)) {
                                 unsigned long long bits;
                                 if (lane < 9u) {
                                         const int row = (lane < 3u) ? (int)(F_POS + lane) :
@@ -241,6 +285,7 @@ __global__ void __launch_bounds__(128, MINB)
                                                 SI(I_RAYLO) = (int)(unsigned)(q & 0xffffffffull);
                                                 SI(I_RAYHI) = (int)(unsigned)(q >> 32);
                                                 mode = MODE_WAIT;
+                                                if (STREAM) t_wait = global_ns();
                                         }
                                 }
                                 if (base + (unsigned long long)need >= A.n) exhausted = true;
@@ -257,7 +302,7 @@ __global__ void __launch_bounds__(128, MINB)
                                         if (w == STREAM_ABORT) {
                                                 mode = MODE_IDLE; /* the host gave up */
                                         } else if (!arrived &&
-                                            (global_ns() - t_start > STREAM_TIMEOUT_NS)) {
+                                            (global_ns() - t_wait > STREAM_TIMEOUT_NS)) {
                                                 /* the copies never came (a fault on the host
                                                  * side): give the GPU back and flag it */
                                                 A.cursor[3] = 1ull;
@@ -265,16 +310,43 @@ __global__ void __launch_bounds__(128, MINB)
                                         }
                                 }
                                 if (arrived && (mode == MODE_WAIT)) {
+                                        /* acquire: the ray was written before the watermark
+                                         * moved past it; no load below may be satisfied
+                                         * before the watermark load above */
+                                        if (STREAM) __threadfence();
                                         const unsigned long long r =
                                             (A.order != NULL) ? A.order[q] : q;
-                                        /* (L2 loads: a streamed ray has just been written by
-                                         * a copy engine, L1 must not serve an older line) */
-                                        const double * p = A.position + 3ull * r;
-                                        const double * d = A.direction + 3ull * r;
-                                        const double pos[3] = { __ldcg(p), __ldcg(p + 1),
-                                                __ldcg(p + 2) };
-                                        const double dir[3] = { __ldcg(d), __ldcg(d + 1),
-                                                __ldcg(d + 2) };
+                                        double pos[3], dir[3];
+                                        if (A.position == NULL) {
+                                                /* ray (i, j) of a fan: the products and sums of
+                                                 * turtle_ecef_from_horizontal, ecef.c:170-177 */
+                                                const unsigned long long per_band = A.fan_naz * A.fan_bundle;
+                                                const unsigned long long rr = r + A.fan_ray0;
+                                                const unsigned long long band = rr / per_band;
+                                                const unsigned long long rem = rr - band * per_band;
+                                                const unsigned long long i = rem / A.fan_bundle;
+                                                const unsigned long long j =
+                                                    band * A.fan_bundle + (rem - i * A.fan_bundle);
+                                                const double2 az = __ldg(A.fan_az + i);
+                                                const double2 el = __ldg(A.fan_el + j);
+                                                const double r0 = el.x * az.x, r1 = el.x * az.y, r2 = el.y;
+#pragma unroll
+                                                for (int c = 0; c < 3; c++) {
+                                                        pos[c] = A.fan_origin[c];
+                                                        dir[c] = r0 * A.fan_e[c] + r1 * A.fan_n[c] +
+                                                            r2 * A.fan_u[c];
+                                                }
+                                        } else {
+                                                /* (L2 loads: a streamed ray has just been written
+                                                 * by a copy engine, L1 must not serve an older line) */
+                                                const double * p = A.position + 3ull * r;
+                                                const double * d = A.direction + 3ull * r;
+#pragma unroll
+                                                for (int c = 0; c < 3; c++) {
+                                                        pos[c] = __ldcg(p + c);
+                                                        dir[c] = __ldcg(d + c);
+                                                }
+                                        }
                                         SF(F_POS) = pos[0];
                                         SF(F_POS + 1) = pos[1];
                                         SF(F_POS + 2) = pos[2];
@@ -296,7 +368,7 @@ __global__ void __launch_bounds__(128, MINB)
                                         if (LLA) {
                                                 SF(F_LASTPOS) = SF(F_LASTPOS + 1) =
                                                     SF(F_LASTPOS + 2) = DBL_MAX;
-                                                tb::lla_reset(lla, G.n_transforms);
+                                                tb::lla_reset(G, V);
                                         }
                                         if (!finite3(pos) || !finite3(dir)) {
                                                 /* never traced: an empty record (position
@@ -327,20 +399,16 @@ __global__ void __launch_bounds__(128, MINB)
                                 continue;
                         }
                 }
-                if ((mode == MODE_IDLE) || (mode == MODE_WAIT) || (mode == MODE_DONE)) continue;
+                const bool active = !((mode == MODE_IDLE) || (mode == MODE_WAIT) || (mode == MODE_DONE));
+                if (!LLA && !active) continue;
 
                 /* ---- exactly one ECEF -> geodetic transform per lane and iteration:
                  * the one of a geometry sample, or -- local approximation on -- one of
-                 * the three finite-difference transforms of a Jacobian rebuild that the
-                 * previous sample requested (stepper.c:144-162). Running the rebuild as
-                 * iterations of its own keeps the lanes of a warp on equal work; inline
-                 * it would make every lane wait for 3 extra transforms whenever ONE lane
-                 * rebuilds. */
-                if (LLA && (SI(I_PEND) != 0) && (mode != MODE_REBUILD)) {
-                        SI(I_RESUME) = mode;
-                        SI(I_RB_AXIS) = 0;
-                        mode = MODE_REBUILD;
-                }
+                 * the three finite-difference transforms of a Jacobian (stepper.c:144-162)
+                 * that went stale when its reference point moved and that the coming
+                 * sample is about to apply (tb::lla_due; lazily: a Jacobian nobody reads
+                 * is never built, see tb::get_geographic). Running the rebuild as
+                 * iterations of its own keeps the lanes of a warp on equal work. */
                 tb::Sample S;
                 /* SHAPE_STACK leaves registers free: the sampled position stays in them, it
                  * IS the new position of a tentative step (same expression, same bits) */
@@ -360,19 +428,10 @@ __global__ void __launch_bounds__(128, MINB)
                         moved[1] = p[1];
                         moved[2] = p[2];
                 } else {
-                        double p[3];
+                        double p[3] = { 0., 0., 0. };
                         int rb_t = 0, rb_axis = 0;
                         bool heavy = true;
-                        if (LLA && (mode == MODE_REBUILD)) {
-                                rb_t = __ffs(SI(I_PEND)) - 1;
-                                rb_axis = SI(I_RB_AXIS);
-                                p[0] = lla[rb_t].ref_ecef[0];
-                                p[1] = lla[rb_t].ref_ecef[1];
-                                p[2] = lla[rb_t].ref_ecef[2];
-                                if (rb_axis == 0) p[0] += 10.;
-                                else if (rb_axis == 1) p[1] += 10.;
-                                else p[2] += 10.;
-                        } else {
+                        if (active && (!LLA || (mode != MODE_REBUILD))) {
                                 double step = 0.; /* MODE_INIT: sample the start position */
                                 if (mode == MODE_TENT) /* stepper.c:824 */
                                         step = SF(F_DS);
@@ -386,34 +445,83 @@ __global__ void __launch_bounds__(128, MINB)
                                         p[1] += SF(F_DIR + 1) * step;
                                         p[2] += SF(F_DIR + 2) * step;
                                 }
-                                heavy = tb::needs_geodetic<LLA>(G, lla, p);
+                                if (LLA) {
+                                        const unsigned due = tb::lla_due(G, V, (unsigned)SI(I_PEND), p);
+                                        if (due != 0u) {
+                                                SI(I_RESUME) = mode;
+                                                SI(I_RB_MASK) = (int)due;
+                                                SI(I_RB_AXIS) = 0;
+                                                mode = MODE_REBUILD;
+                                        }
+                                }
+                        }
+                        if (LLA) {
+                                /* ---- light and heavy iterations. A sample in range of its
+                                 * reference points is LIGHT: no transform, no projection,
+                                 * a tenth of the instructions of the others (samples out of
+                                 * range, Jacobian columns). Near the ground, where the steps
+                                 * are shorter than the range, light samples come in long
+                                 * runs (a bisection is 23 of them) and are half of all
+                                 * samples -- one per iteration next to a heavy lane, each
+                                 * would cost its warp a heavy iteration. So while enough
+                                 * lanes are light the heavy ones sit the iteration out
+                                 * (bounded, so that none starves): the light runs are
+                                 * consumed at their own cost, and the heavy iterations
+                                 * that follow find most lanes heavy. Warp uniform. */
+                                const bool hv = active && ((mode == MODE_REBUILD) ||
+                                                              !tb::lla_all_in_range(G, V, p));
+                                const unsigned heavy_lanes = __ballot_sync(FULL, hv);
+                                const unsigned light_lanes = __ballot_sync(FULL, active && !hv);
+                                bool parked = false;
+                                if ((heavy_lanes != 0u) && (__popc(light_lanes) >= LIGHT_MIN) &&
+                                    (hold < HOLD_MAX)) {
+                                        hold++;
+                                        parked = hv;
+                                } else {
+                                        hold = 0;
+                                }
+                                if (!active || parked) continue;
+                        }
+                        if (LLA && (mode == MODE_REBUILD)) {
+                                rb_t = __ffs(SI(I_RB_MASK)) - 1;
+                                rb_axis = SI(I_RB_AXIS);
+                                const int row0 = G.lla_row[rb_t];
+                                p[0] = tb::lla_at(V, row0);
+                                p[1] = tb::lla_at(V, row0 + 1);
+                                p[2] = tb::lla_at(V, row0 + 2);
+                                if (rb_axis == 0) p[0] += 10.;
+                                else if (rb_axis == 1) p[1] += 10.;
+                                else p[2] += 10.;
+                        } else {
+                                heavy = tb::needs_geodetic<LLA>(G, V, p);
                         }
                         double pre[3] = { 0., 0., 0. };
                         if (heavy) tb::geodetic_with_geoid(G, p, pre);
                         if (LLA && (mode == MODE_REBUILD)) {
-                                tb::rebuild_column<PROJ>(G, lla[rb_t], G.transforms[rb_t],
-                                    ((SI(I_PEND_N0) >> rb_t) & 1) ? 3 : 0, rb_axis, pre);
+                                tb::rebuild_column<PROJ>(G, V, rb_t, rb_axis, pre);
+                                if (LLA_COUNT) my_rebuilds++;
                                 if (rb_axis == 2) {
+                                        SI(I_RB_MASK) &= ~(1 << rb_t);
                                         SI(I_PEND) &= ~(1 << rb_t);
                                         SI(I_RB_AXIS) = 0;
-                                        if (SI(I_PEND) == 0) mode = SI(I_RESUME);
+                                        if (SI(I_RB_MASK) == 0) mode = SI(I_RESUME);
                                 } else {
                                         SI(I_RB_AXIS) = rb_axis + 1;
                                 }
                                 continue;
                         }
                         double last_pos[3] = { 0., 0., 0. };
+                        unsigned stale = 0u;
                         if (LLA) {
                                 last_pos[0] = SF(F_LASTPOS);
                                 last_pos[1] = SF(F_LASTPOS + 1);
                                 last_pos[2] = SF(F_LASTPOS + 2);
+                                stale = (unsigned)SI(I_PEND);
                         }
-                        tb::Pending pending = { 0u, 0u };
-                        tb::sample_geometry<LLA, PROJ, true>(G, lla, last_pos,
-                            mode != MODE_BISECT, p, S, heavy ? pre : NULL, &pending);
+                        tb::sample_geometry<LLA, PROJ, true>(G, V, stale, last_pos,
+                            mode != MODE_BISECT, p, S, heavy ? pre : NULL);
                         if (LLA) {
-                                SI(I_PEND) = (int)pending.mask;
-                                SI(I_PEND_N0) = (int)pending.n0;
+                                SI(I_PEND) = (int)stale;
                                 if (mode != MODE_BISECT) {
                                         SF(F_LASTPOS) = last_pos[0];
                                         SF(F_LASTPOS + 1) = last_pos[1];
@@ -547,15 +655,18 @@ __global__ void __launch_bounds__(128, MINB)
 #undef SF
 #undef SI
 
-        /* per-warp counters */
-        unsigned long long steps64 = my_steps, samples64 = my_samples;
+        /* per-warp counters ([3] is the time-out flag of a streamed call; Jacobian-column
+         * iterations are counted with the samples' cursor block, slot [4]) */
+        unsigned long long steps64 = my_steps, samples64 = my_samples, rebuilds64 = my_rebuilds;
         for (int o = 16; o > 0; o >>= 1) {
                 steps64 += __shfl_down_sync(FULL, steps64, o);
                 samples64 += __shfl_down_sync(FULL, samples64, o);
+                if (LLA) rebuilds64 += __shfl_down_sync(FULL, rebuilds64, o);
         }
         if (lane == 0u) {
                 atomicAdd(A.cursor + 1, steps64);
                 atomicAdd(A.cursor + 2, samples64);
+                if (LLA) atomicAdd(A.cursor + 4, rebuilds64);
         }
 }
 
@@ -584,21 +695,21 @@ __global__ void schedule_key_kernel(unsigned long long n, const double * __restr
         }
 }
 
-/* Device-side particle states of turtle_stepper_step_batch.
- * (1) The last sample: a structure of arrays of doubles, field f of particle i at
- *     states[f * stride + i], so that the lanes of a warp (consecutive particles) read
- *     and write whole sectors. Fields: last position (3), lat / lon / alt / elev0 /
- *     elev1 (5), the two indices packed in one slot (1).
- * (2) The local approximations: one tb::LlaState per particle and transform, used IN
- *     PLACE by the core functions. A step usually only reads the reference point (one
- *     32-byte sector) to find that it is out of range; the Jacobian is touched when it
- *     is applied or rebuilt. */
-enum { PS_LASTPOS = 0, PS_LAT = 3, PS_LON, PS_ALT, PS_ELEV0, PS_ELEV1, PS_INDEX, PS_FIELDS };
+/* Device-side particle states of turtle_stepper_step_batch: what `struct turtle_stepper`
+ * remembers for ONE track between two calls, FIELD-MAJOR -- field f of particle i at
+ * states[f * stride + i] -- so that the lanes of a warp (consecutive particles) read and
+ * write whole sectors. Fields: last position (3), lat / lon / alt / elev0 / elev1 (5), the
+ * two indices packed in one slot (1), the stale-Jacobian mask of the local approximation
+ * (1), then the G.lla_rows rows of the local approximations themselves (tb::LlaView with
+ * this very stride: the core functions use them IN PLACE -- a step usually only reads the
+ * reference point to find that it is out of range; the Jacobian is touched when it is
+ * applied or rebuilt). */
+enum { PS_LASTPOS = 0, PS_LAT = 3, PS_LON, PS_ALT, PS_ELEV0, PS_ELEV1, PS_INDEX, PS_STALE,
+       PS_FIELDS };
 
 struct StepArgs {
         unsigned long long n;
         double * states; /* or NULL */
-        tb::LlaState * lla_states; /* [n][n_transforms], with `states` */
         unsigned long long stride;
         double * position;
         const double * direction; /* or NULL: query mode */
@@ -615,14 +726,16 @@ struct StepArgs {
  * sample-granular scheduling as the trace kernel: persistent lanes pull particles from
  * a queue; every loop iteration evaluates one stepper_sample per lane (start sample
  * unless the particle's cached last sample is at its position, tentative end, bisection
- * mid-points); a particle that is done writes its outputs and state and its lane is
- * refilled. Step-granular lockstep (one thread = one whole step) would make every warp
- * pay the 23-sample bisection of its unluckiest lane on most steps. */
+ * mid-points) or one column of a stale Jacobian that the coming sample will read; a
+ * particle that is done writes its outputs and state and its lane is refilled.
+ * Step-granular lockstep (one thread = one whole step) would make every warp pay the
+ * 23-sample bisection of its unluckiest lane on most steps. */
 template <bool LLA, bool PROJ>
 __global__ void __launch_bounds__(128, 5)
     walk_kernel(const __grid_constant__ tb::Geometry G, const StepArgs A)
 {
         __shared__ LaneStore store;
+        extern __shared__ double lla_store[]; /* LLA without device states: scratch */
         const unsigned tid = threadIdx.x;
         const unsigned lane = tid & 31u;
         const unsigned FULL = 0xffffffffu;
@@ -630,10 +743,11 @@ __global__ void __launch_bounds__(128, 5)
 #define SI(k) store.i[k][tid]
 
         int mode = MODE_IDLE;
-        tb::LlaState lla_local[LLA ? tb::MAX_TRANSFORMS : 1]; /* when no states are kept */
-        tb::LlaState * lla = lla_local;
-        unsigned my_steps = 0u, my_samples = 0u;
+        tb::LlaView V = { lla_store + tid, 128 };
+        unsigned my_steps = 0u, my_samples = 0u, my_rebuilds = 0u;
         bool exhausted = false;
+        int hold = 0; /* LLA, warp uniform: light iterations since the last heavy one */
+        constexpr int LIGHT_MIN = 5, HOLD_MAX = 24;
 
         for (;;) {
                 bool started = false; /* the start sample is available in the lane store */
@@ -664,21 +778,24 @@ __global__ void __launch_bounds__(128, 5)
                                                         SF(F_DIR + 2) = A.direction[3 * r + 2];
                                                 }
                                                 double lp[3] = { DBL_MAX, DBL_MAX, DBL_MAX };
+                                                SI(I_PEND) = 0;
                                                 if (A.states != NULL) {
                                                         const double * ps = A.states + r;
                                                         lp[0] = ps[(PS_LASTPOS + 0) * A.stride];
                                                         lp[1] = ps[(PS_LASTPOS + 1) * A.stride];
                                                         lp[2] = ps[(PS_LASTPOS + 2) * A.stride];
-                                                        if (LLA)
-                                                                lla = A.lla_states +
-                                                                    r * (unsigned long long)G.n_transforms;
+                                                        if (LLA) {
+                                                                V.base = A.states + PS_FIELDS * A.stride + r;
+                                                                V.stride = A.stride;
+                                                                SI(I_PEND) = __double2loint(
+                                                                    ps[PS_STALE * A.stride]);
+                                                        }
                                                 } else if (LLA) {
-                                                        tb::lla_reset(lla, G.n_transforms);
+                                                        tb::lla_reset(G, V);
                                                 }
                                                 SF(F_LASTPOS) = lp[0];
                                                 SF(F_LASTPOS + 1) = lp[1];
                                                 SF(F_LASTPOS + 2) = lp[2];
-                                                SI(I_PEND) = 0;
                                                 mode = MODE_INIT;
                                                 /* stepper.c:708-710: exact cache test */
                                                 if ((pos[0] == lp[0]) && (pos[1] == lp[1]) &&
@@ -703,59 +820,82 @@ __global__ void __launch_bounds__(128, 5)
                                 continue;
                         }
                 }
-                if (mode == MODE_IDLE) continue;
+                const bool active = mode != MODE_IDLE;
+                if (!LLA && !active) continue;
 
-                /* a Jacobian rebuild requested by the previous sample runs first, one
-                 * transform per iteration (see trace_kernel) */
-                if (LLA && !started && (SI(I_PEND) != 0) && (mode != MODE_REBUILD)) {
-                        SI(I_RESUME) = mode;
-                        SI(I_RB_AXIS) = 0;
-                        mode = MODE_REBUILD;
+                /* the position of the coming sample (none: idle lane, cached start sample,
+                 * Jacobian column) */
+                double p[3] = { 0., 0., 0. };
+                const bool sampling = active && !started;
+                if (sampling && (!LLA || (mode != MODE_REBUILD))) {
+                        double step = 0.;
+                        if (mode == MODE_TENT)
+                                step = SF(F_DS);
+                        else if (mode == MODE_BISECT)
+                                step = 0.5 * (SF(F_DS0) + SF(F_DS1));
+                        p[0] = SF(F_POS);
+                        p[1] = SF(F_POS + 1);
+                        p[2] = SF(F_POS + 2);
+                        if (mode != MODE_INIT) {
+                                p[0] += SF(F_DIR) * step;
+                                p[1] += SF(F_DIR + 1) * step;
+                                p[2] += SF(F_DIR + 2) * step;
+                        }
+                        if (LLA) { /* a stale Jacobian about to be read? */
+                                const unsigned due = tb::lla_due(G, V, (unsigned)SI(I_PEND), p);
+                                if (due != 0u) {
+                                        SI(I_RESUME) = mode;
+                                        SI(I_RB_MASK) = (int)due;
+                                        SI(I_RB_AXIS) = 0;
+                                        mode = MODE_REBUILD;
+                                }
+                        }
                 }
-                if (mode == MODE_FINISH) { /* a finished particle whose rebuild is done */
-                        finish = true;
-                        step_out = SF(F_DS0);
-                } else if (!started) {
+                if (LLA) { /* light and heavy iterations: see trace_kernel (warp wide) */
+                        const bool hv = sampling && ((mode == MODE_REBUILD) ||
+                                                        !tb::lla_all_in_range(G, V, p));
+                        const unsigned heavy_lanes = __ballot_sync(FULL, hv);
+                        const unsigned light_lanes = __ballot_sync(FULL, active && !hv);
+                        bool parked = false;
+                        if ((heavy_lanes != 0u) && (__popc(light_lanes) >= LIGHT_MIN) &&
+                            (hold < HOLD_MAX)) {
+                                hold++;
+                                parked = hv;
+                        } else {
+                                hold = 0;
+                        }
+                        if (!active || parked) continue;
+                }
+
+                if (!started) {
                         /* ---- one ECEF -> geodetic transform ------------------------- */
                         tb::Sample S;
                         {
-                                double p[3];
                                 int rb_t = 0, rb_axis = 0;
                                 bool heavy = true;
                                 if (LLA && (mode == MODE_REBUILD)) {
-                                        rb_t = __ffs(SI(I_PEND)) - 1;
+                                        rb_t = __ffs(SI(I_RB_MASK)) - 1;
                                         rb_axis = SI(I_RB_AXIS);
-                                        p[0] = lla[rb_t].ref_ecef[0];
-                                        p[1] = lla[rb_t].ref_ecef[1];
-                                        p[2] = lla[rb_t].ref_ecef[2];
+                                        const int row0 = G.lla_row[rb_t];
+                                        p[0] = tb::lla_at(V, row0);
+                                        p[1] = tb::lla_at(V, row0 + 1);
+                                        p[2] = tb::lla_at(V, row0 + 2);
                                         if (rb_axis == 0) p[0] += 10.;
                                         else if (rb_axis == 1) p[1] += 10.;
                                         else p[2] += 10.;
                                 } else {
-                                        double step = 0.;
-                                        if (mode == MODE_TENT)
-                                                step = SF(F_DS);
-                                        else if (mode == MODE_BISECT)
-                                                step = 0.5 * (SF(F_DS0) + SF(F_DS1));
-                                        p[0] = SF(F_POS);
-                                        p[1] = SF(F_POS + 1);
-                                        p[2] = SF(F_POS + 2);
-                                        if (mode != MODE_INIT) {
-                                                p[0] += SF(F_DIR) * step;
-                                                p[1] += SF(F_DIR + 1) * step;
-                                                p[2] += SF(F_DIR + 2) * step;
-                                        }
-                                        heavy = tb::needs_geodetic<LLA>(G, lla, p);
+                                        heavy = tb::needs_geodetic<LLA>(G, V, p);
                                 }
                                 double pre[3] = { 0., 0., 0. };
                                 if (heavy) tb::geodetic_with_geoid(G, p, pre);
                                 if (LLA && (mode == MODE_REBUILD)) {
-                                        tb::rebuild_column<PROJ>(G, lla[rb_t], G.transforms[rb_t],
-                                            ((SI(I_PEND_N0) >> rb_t) & 1) ? 3 : 0, rb_axis, pre);
+                                        tb::rebuild_column<PROJ>(G, V, rb_t, rb_axis, pre);
+                                        my_rebuilds++;
                                         if (rb_axis == 2) {
+                                                SI(I_RB_MASK) &= ~(1 << rb_t);
                                                 SI(I_PEND) &= ~(1 << rb_t);
                                                 SI(I_RB_AXIS) = 0;
-                                                if (SI(I_PEND) == 0) mode = SI(I_RESUME);
+                                                if (SI(I_RB_MASK) == 0) mode = SI(I_RESUME);
                                         } else {
                                                 SI(I_RB_AXIS) = rb_axis + 1;
                                         }
@@ -763,13 +903,10 @@ __global__ void __launch_bounds__(128, 5)
                                 }
                                 double last_pos[3] = { SF(F_LASTPOS), SF(F_LASTPOS + 1),
                                         SF(F_LASTPOS + 2) };
-                                tb::Pending pending = { 0u, 0u };
-                                tb::sample_geometry<LLA, PROJ, true>(G, lla, last_pos,
-                                    mode != MODE_BISECT, p, S, heavy ? pre : NULL, &pending);
-                                if (LLA) {
-                                        SI(I_PEND) = (int)pending.mask;
-                                        SI(I_PEND_N0) = (int)pending.n0;
-                                }
+                                unsigned stale = LLA ? (unsigned)SI(I_PEND) : 0u;
+                                tb::sample_geometry<LLA, PROJ, true>(G, V, stale, last_pos,
+                                    mode != MODE_BISECT, p, S, heavy ? pre : NULL);
+                                if (LLA) SI(I_PEND) = (int)stale;
                                 if (mode != MODE_BISECT) {
                                         SF(F_LASTPOS) = last_pos[0];
                                         SF(F_LASTPOS + 1) = last_pos[1];
@@ -859,15 +996,9 @@ __global__ void __launch_bounds__(128, 5)
                         }
                 }
                 if (!finish) continue;
-                if (LLA && (SI(I_PEND) != 0)) {
-                        /* the state to save must include the pending Jacobian: finish
-                         * once the rebuild iterations are through */
-                        SF(F_DS0) = step_out;
-                        mode = MODE_FINISH;
-                        continue;
-                }
 
-                /* ---- outputs and state of a finished particle ---------------------- */
+                /* ---- outputs and state of a finished particle (a Jacobian that is still
+                 * stale stays so: the mask is part of the state) ------------------------ */
                 const unsigned long long r = ((unsigned long long)(unsigned)SI(I_RAYHI) << 32) |
                     (unsigned long long)(unsigned)SI(I_RAYLO);
                 const int idx0 = SI(I_IDX0);
@@ -899,26 +1030,31 @@ __global__ void __launch_bounds__(128, 5)
                         ps[PS_ELEV0 * A.stride] = SF(F_ELEV0);
                         ps[PS_ELEV1 * A.stride] = SF(F_ELEV1);
                         ps[PS_INDEX * A.stride] = __hiloint2double(SI(I_IDX1), idx0);
+                        if (LLA) ps[PS_STALE * A.stride] = __hiloint2double(0, SI(I_PEND));
+                        V.base = lla_store + tid;
+                        V.stride = 128;
                 }
                 mode = MODE_IDLE;
         }
 #undef SF
 #undef SI
-        unsigned long long steps64 = my_steps, samples64 = my_samples;
+        unsigned long long steps64 = my_steps, samples64 = my_samples, rebuilds64 = my_rebuilds;
         for (int o = 16; o > 0; o >>= 1) {
                 steps64 += __shfl_down_sync(FULL, steps64, o);
                 samples64 += __shfl_down_sync(FULL, samples64, o);
+                rebuilds64 += __shfl_down_sync(FULL, rebuilds64, o);
         }
         if (lane == 0u) {
                 atomicAdd(A.counters + 1, steps64);
                 atomicAdd(A.counters + 2, samples64);
+                atomicAdd(A.counters + 4, rebuilds64);
         }
 }
 
 /* turtle_stepper_reset for every particle (stepper.c:602-615): last position and every
- * reference point at DBL_MAX; the last sample is cleared. */
-__global__ void states_reset_kernel(double * states, tb::LlaState * lla_states,
-    unsigned long long stride, unsigned long long n, int n_transforms)
+ * reference point at DBL_MAX; the last sample is cleared, no Jacobian is stale. */
+__global__ void states_reset_kernel(const __grid_constant__ tb::Geometry G, double * states,
+    unsigned long long stride, unsigned long long n)
 {
         const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
         for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -927,7 +1063,9 @@ __global__ void states_reset_kernel(double * states, tb::LlaState * lla_states,
                 for (int k = 0; k < 3; k++) ps[(PS_LASTPOS + k) * stride] = DBL_MAX;
                 for (int k = PS_LAT; k < PS_INDEX; k++) ps[k * stride] = 0.;
                 ps[PS_INDEX * stride] = __hiloint2double(-1, -1);
-                tb::lla_reset(lla_states + i * (unsigned long long)n_transforms, n_transforms);
+                ps[PS_STALE * stride] = __hiloint2double(0, 0);
+                const tb::LlaView V = { states + PS_FIELDS * stride + i, (size_t)stride };
+                tb::lla_reset(G, V);
         }
 }
 
@@ -1244,6 +1382,10 @@ __global__ void __launch_bounds__(256) dfma_kernel(double * out, int iterations)
 
 namespace {
 const int N_SLOTS = 3;              /* host-pointer pipeline depth */
+const int DEV_SLOTS = 8;            /* device-pointer calls that may be in flight per plan */
+const int ALL_SLOTS = N_SLOTS + DEV_SLOTS;
+const int CTR = 8;                  /* counters per launch: [0] queue cursor, [1] steps,
+                                     * [2] samples, [3] stream time-out, [4] Jacobian columns */
 const size_t CHUNK_RAYS = 1u << 20; /* rays per pipeline chunk (one kernel per chunk) */
 const int STREAM_CHUNK_SHIFT = 18;  /* rays per copy of a streamed call: 256 Ki */
 const size_t STREAM_CHUNK_RAYS = (size_t)1 << STREAM_CHUNK_SHIFT;
@@ -1262,15 +1404,16 @@ struct turtle_plan {
         size_t bytes;
         turtle_residency_report report;
         std::vector<struct turtle_stack *> pinned;
-        unsigned long long * d_counters; /* N_SLOTS + 1 triplets */
+        unsigned long long * d_counters; /* ALL_SLOTS blocks of CTR counters */
+        int dev_slot;                    /* block of the latest device-pointer call */
         turtle_plan_counters counters;
         /* ray scheduling (turtle_plan_schedule_set) */
         int schedule;
         int specialise; /* turtle_plan_specialise_set */
         int pipeline_mode; /* turtle_plan_pipeline_set */
-        unsigned * d_sched[4]; /* per pipeline slot: keys, index, keys', order */
-        void * d_sched_tmp[4];
-        size_t sched_rays[4], sched_tmp_bytes[4];
+        unsigned * d_sched[ALL_SLOTS]; /* per slot: keys, index, keys', order */
+        void * d_sched_tmp[ALL_SLOTS];
+        size_t sched_rays[ALL_SLOTS], sched_tmp_bytes[ALL_SLOTS];
         /* host-pointer pipeline */
         cudaStream_t stream[N_SLOTS];
         cudaEvent_t ev0[N_SLOTS], ev1[N_SLOTS];
@@ -1280,22 +1423,27 @@ struct turtle_plan {
         /* streamed host-pointer calls (trace_streamed) */
         double * d_all_in;
         turtle_trace_result * d_all_out;
-        size_t all_rays;
+        size_t all_rays, all_records;
         unsigned long long * d_stream_state; /* watermark + per-chunk counters */
         unsigned long long * h_marks;        /* pinned: the watermark values to copy */
         unsigned * h_flags;                  /* pinned + mapped: chunk completion flags */
         size_t stream_chunks;
         cudaEvent_t ev_reset;
         cudaStream_t drain[4]; /* N_DRAINS result streams */
+        /* fan tables (turtle_stepper_trace_fan), per slot: pinned host copy + device copy */
+        double2 * h_fan[ALL_SLOTS];
+        double2 * d_fan[ALL_SLOTS];
+        size_t fan_angles[ALL_SLOTS];
+        /* device staging of the field arrays of a host-pointer call */
+        void * d_field_pool;
+        size_t field_pool_bytes;
 };
 
 struct turtle_states {
         struct turtle_plan * plan;
         size_t n;
-        double * d_states;
-        tb::LlaState * d_lla;
-        size_t stride; /* particles per field row */
-        int n_transforms;
+        double * d_states; /* PS_FIELDS + G.lla_rows field rows of `stride` particles */
+        size_t stride;
 };
 
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -1438,10 +1586,11 @@ static enum turtle_return freeze_plan(turtle_function_t * fn, struct turtle_step
         plan->d_maps = NULL;
         plan->d_tiles = NULL;
         plan->d_counters = NULL;
+        plan->dev_slot = N_SLOTS;
         plan->schedule = 0;
         plan->specialise = 1;
         plan->pipeline_mode = 0;
-        for (int s = 0; s < 4; s++) {
+        for (int s = 0; s < ALL_SLOTS; s++) {
                 plan->d_sched[s] = NULL;
                 plan->d_sched_tmp[s] = NULL;
                 plan->sched_rays[s] = 0;
@@ -1456,12 +1605,20 @@ static enum turtle_return freeze_plan(turtle_function_t * fn, struct turtle_step
         plan->d_all_in = NULL;
         plan->d_all_out = NULL;
         plan->all_rays = 0;
+        plan->all_records = 0;
         plan->d_stream_state = NULL;
         plan->h_marks = NULL;
         plan->h_flags = NULL;
         plan->stream_chunks = 0;
         plan->ev_reset = NULL;
         for (int j = 0; j < 4; j++) plan->drain[j] = NULL;
+        for (int k = 0; k < ALL_SLOTS; k++) {
+                plan->h_fan[k] = NULL;
+                plan->d_fan[k] = NULL;
+                plan->fan_angles[k] = 0;
+        }
+        plan->d_field_pool = NULL;
+        plan->field_pool_bytes = 0;
         cudaDeviceProp prop;
         cudaGetDeviceProperties(&prop, device);
         plan->sm_count = prop.multiProcessorCount;
@@ -1549,7 +1706,7 @@ static enum turtle_return freeze_plan(turtle_function_t * fn, struct turtle_step
                     cudaMemcpyHostToDevice);
         if (err == cudaSuccess)
                 err = cudaMalloc((void **)&plan->d_counters,
-                    (N_SLOTS + 1) * 4 * sizeof(unsigned long long));
+                    ALL_SLOTS * CTR * sizeof(unsigned long long));
         if (err != cudaSuccess) {
                 turtle_plan_destroy(&plan);
                 return tbh::raise(fn, TURTLE_RETURN_LIBRARY_ERROR, BATCH_CU, __LINE__,
@@ -1662,12 +1819,17 @@ extern "C" void turtle_plan_destroy(struct turtle_plan ** plan_)
                 cudaFree(plan->d_in[s]);
                 cudaFree(plan->d_out[s]);
         }
-        for (int s = 0; s < 4; s++) {
+        for (int s = 0; s < ALL_SLOTS; s++) {
                 cudaFree(plan->d_sched[s]);
                 cudaFree(plan->d_sched_tmp[s]);
         }
         cudaFree(plan->d_all_in);
         cudaFree(plan->d_all_out);
+        cudaFree(plan->d_field_pool);
+        for (int k = 0; k < ALL_SLOTS; k++) {
+                if (plan->h_fan[k] != NULL) cudaFreeHost(plan->h_fan[k]);
+                cudaFree(plan->d_fan[k]);
+        }
         cudaFree(plan->d_stream_state);
         if (plan->h_marks != NULL) cudaFreeHost(plan->h_marks);
         if (plan->h_flags != NULL) cudaFreeHost(plan->h_flags);
@@ -1754,12 +1916,27 @@ static cudaError_t schedule_rays(struct turtle_plan * plan, int slot, size_t n,
         return err;
 }
 
-/* Grid of the persistent kernel: a multiple of the SM count. */
+/* Dynamic shared memory of a kernel of the local approximation: G.lla_rows columns of
+ * 128 doubles (tb::LlaView). */
+static size_t lla_bytes(const struct turtle_plan * plan)
+{
+        return (plan->G.range > 0.) ? (size_t)plan->G.lla_rows * 128 * sizeof(double) : 0;
+}
+
+/* Grid of the persistent kernel: a multiple of the SM count. With the local approximation
+ * the lane store of a CTA grows by the state of the transforms the geometry uses, and the
+ * CTAs per SM are what fits the 227 kB of shared memory (4 for one projected transform). */
 static int trace_grid(const struct turtle_plan * plan, size_t n, int * blocks, int * threads)
 {
         *threads = (plan->threads > 0) ? round_up(plan->threads, 32) : 128;
         if (*threads > 128) *threads = 128; /* __launch_bounds__(128, .) */
-        const int per_sm = (plan->ctas_per_sm > 0) ? plan->ctas_per_sm : 6;
+        int per_sm = (plan->ctas_per_sm > 0) ? plan->ctas_per_sm : 6;
+        if (plan->G.range > 0.) {
+                const size_t cta = sizeof(LaneStoreT<N_F_LLA, N_I>) + lla_bytes(plan) + 1024;
+                const int fit = (int)((227 * 1024) / cta);
+                if (per_sm > fit) per_sm = (fit > 0) ? fit : 1;
+                if (per_sm > 4) per_sm = 4; /* the register budget these kernels are built for */
+        }
         long long want = (long long)plan->sm_count * per_sm;
         const long long need = (long long)((n + *threads - 1) / *threads);
         if (need < want) want = (need > 0) ? need : 1;
@@ -1785,23 +1962,38 @@ static void trace_start(const struct turtle_plan * plan, int per_sm, int blocks,
 {
         void (*kernel)(const tb::Geometry, const TraceArgs) =
             trace_kernel<LLA, PROJ, MINB, SHAPE, STREAM>;
+        const size_t dynamic = LLA ? lla_bytes(plan) : 0;
         static int carveout_of[16] = { 0 };
+        static size_t dynamic_of[16] = { 0 };
         const int key = per_sm & 15;
-        if (carveout_of[key] == 0) {
+        if ((carveout_of[key] == 0) || (dynamic_of[key] != dynamic)) {
                 cudaFuncAttributes attr;
                 if (cudaFuncGetAttributes(&attr, kernel) == cudaSuccess) {
-                        const size_t need = (size_t)per_sm * (attr.sharedSizeBytes + 1024);
+                        const size_t need = (size_t)per_sm * (attr.sharedSizeBytes + dynamic + 1024);
                         int percent = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
                         if (percent > 100) percent = 100;
                         carveout_of[key] = percent + 1;
                 } else {
                         carveout_of[key] = 101;
                 }
+                dynamic_of[key] = dynamic;
                 cudaGetLastError();
         }
+        if (dynamic > 0)
+                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                    (int)dynamic);
         cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
             carveout_of[key] - 1);
-        kernel<<<blocks, threads, 0, stream>>>(plan->G, A);
+        kernel<<<blocks, threads, dynamic, stream>>>(plan->G, A);
+}
+
+/* Device-pointer calls are asynchronous: up to DEV_SLOTS of them may be in flight on a
+ * plan (on different streams -- how a caller backfills the tail of one batch with the
+ * head of the next); each takes the next counter block / schedule buffers of the ring. */
+static int next_device_slot(struct turtle_plan * plan)
+{
+        plan->dev_slot = N_SLOTS + (plan->dev_slot - N_SLOTS + 1) % DEV_SLOTS;
+        return plan->dev_slot;
 }
 
 /* Device state of a streamed call: [0] watermark, then one counter per chunk. */
@@ -1812,15 +2004,32 @@ struct StreamState {
         unsigned * chunk_flags;
 };
 
+/* Device tables of a fan: sines / cosines of its angles and the frame of its station. */
+struct FanTables {
+        const double2 * az;
+        const double2 * el;
+        double origin[3], e[3], n[3], u[3];
+        unsigned long long naz, bundle, ray0;
+};
+
+/* What one launch reads and writes: DEVICE memory throughout. */
+struct DeviceIo {
+        const double * position;  /* with `direction`, or both NULL: a fan */
+        const double * direction;
+        const FanTables * fan;
+        struct turtle_trace_result * results; /* or NULL */
+        const struct turtle_trace_fields * fields; /* or NULL */
+};
+
 static cudaError_t launch_trace(struct turtle_plan * plan, int slot, size_t n,
-    const double * d_position, const double * d_direction,
-    const struct turtle_trace_rule * rule, struct turtle_trace_result * d_results,
+    const DeviceIo & io, const struct turtle_trace_rule * rule,
     unsigned long long * d_counters, cudaStream_t stream, const StreamState * streamed = NULL,
     turtle_trace_crossing * d_crossings = NULL, int max_crossings = 0)
 {
-        cudaError_t err = cudaMemsetAsync(d_counters, 0x0, 4 * sizeof(unsigned long long), stream);
+        cudaError_t err = cudaMemsetAsync(d_counters, 0x0, CTR * sizeof(unsigned long long), stream);
         if (err != cudaSuccess) return err;
         TraceArgs A;
+        memset(&A, 0x0, sizeof A);
         A.n = n;
         A.chunk_shift = (streamed != NULL) ? streamed->chunk_shift : 0;
         A.watermark = (streamed != NULL) ? streamed->watermark : NULL;
@@ -1829,12 +2038,28 @@ static cudaError_t launch_trace(struct turtle_plan * plan, int slot, size_t n,
         A.crossings = d_crossings;
         A.max_crossings = max_crossings;
         A.order = NULL;
-        if (streamed == NULL)
-                err = schedule_rays(plan, slot, n, d_position, d_direction, stream, &A.order);
+        if ((streamed == NULL) && (io.fan == NULL))
+                err = schedule_rays(plan, slot, n, io.position, io.direction, stream, &A.order);
         if (err != cudaSuccess) return err;
-        A.position = d_position;
-        A.direction = d_direction;
-        A.results = d_results;
+        A.position = io.position;
+        A.direction = io.direction;
+        if (io.fan != NULL) {
+                A.position = A.direction = NULL;
+                A.fan_az = io.fan->az;
+                A.fan_el = io.fan->el;
+                for (int c = 0; c < 3; c++) {
+                        A.fan_origin[c] = io.fan->origin[c];
+                        A.fan_e[c] = io.fan->e[c];
+                        A.fan_n[c] = io.fan->n[c];
+                        A.fan_u[c] = io.fan->u[c];
+                }
+                A.fan_naz = io.fan->naz;
+                A.fan_bundle = io.fan->bundle;
+                A.fan_ray0 = io.fan->ray0;
+        }
+        A.results = io.results;
+        A.use_fields = (io.fields != NULL);
+        if (io.fields != NULL) A.fields = *io.fields;
         A.cursor = d_counters;
         A.altitude_min = rule->altitude_min;
         A.altitude_max = rule->altitude_max;
@@ -1846,36 +2071,37 @@ static cudaError_t launch_trace(struct turtle_plan * plan, int slot, size_t n,
         bool proj = false; /* any projected map? else the projection code is compiled out */
         for (int t = 0; t < plan->G.n_transforms; t++)
                 if (plan->G.transforms[t].type != tb::PROJ_GEODETIC) proj = true;
+        /* the register budget follows the requested residency (in units of 128 threads);
+         * the kernels of the local approximation are built for 4 CTAs per SM (trace_grid) */
 #define TRACE_LAUNCH(MINB)                                                             \
         do {                                                                           \
-                if (lla && proj)                                                       \
-                        trace_start<true, true, MINB, tb::SHAPE_GENERIC>(plan, per_sm, blocks, threads, stream, A); \
-                else if (lla)                                                          \
-                        trace_start<true, false, MINB, tb::SHAPE_GENERIC>(plan, per_sm, blocks, threads, stream, A); \
-                else if (proj)                                                         \
+                if (proj)                                                              \
                         trace_start<false, true, MINB, tb::SHAPE_GENERIC>(plan, per_sm, blocks, threads, stream, A); \
                 else                                                                   \
                         trace_start<false, false, MINB, tb::SHAPE_GENERIC>(plan, per_sm, blocks, threads, stream, A); \
         } while (0)
-        /* the register budget follows the requested residency (in units of 128 threads) */
         const int minb = per_sm * threads / 128;
         const bool stack_shape = plan->specialise && (tb::geometry_shape(plan->G) == tb::SHAPE_STACK);
         if (streamed != NULL) {
                 /* streamed calls: the kernels waiting for their rays, 6 CTAs per SM */
-                const int cap = plan->sm_count * 6;
+                const int cap = plan->sm_count * ((per_sm < 6) ? per_sm : 6);
                 if (blocks > cap) blocks = cap;
                 const int sm6 = (per_sm < 6) ? per_sm : 6;
                 if (stack_shape)
                         trace_start<false, false, 6, tb::SHAPE_STACK, true>(plan, sm6, blocks, threads, stream, A);
                 else if (lla && proj)
-                        trace_start<true, true, 6, tb::SHAPE_GENERIC, true>(plan, sm6, blocks, threads, stream, A);
+                        trace_start<true, true, 4, tb::SHAPE_GENERIC, true>(plan, sm6, blocks, threads, stream, A);
                 else if (lla)
-                        trace_start<true, false, 6, tb::SHAPE_GENERIC, true>(plan, sm6, blocks, threads, stream, A);
+                        trace_start<true, false, 4, tb::SHAPE_GENERIC, true>(plan, sm6, blocks, threads, stream, A);
                 else if (proj)
                         trace_start<false, true, 6, tb::SHAPE_GENERIC, true>(plan, sm6, blocks, threads, stream, A);
                 else
                         trace_start<false, false, 6, tb::SHAPE_GENERIC, true>(plan, sm6, blocks, threads, stream, A);
-        } else if (stack_shape) {
+        } else if (lla && proj)
+                trace_start<true, true, 4, tb::SHAPE_GENERIC>(plan, per_sm, blocks, threads, stream, A);
+        else if (lla)
+                trace_start<true, false, 4, tb::SHAPE_GENERIC>(plan, per_sm, blocks, threads, stream, A);
+        else if (stack_shape) {
                 if (minb <= 6)
                         trace_start<false, false, 6, tb::SHAPE_STACK>(plan, per_sm, blocks, threads, stream, A);
                 else
@@ -1904,9 +2130,11 @@ extern "C" enum turtle_return turtle_stepper_trace_batch_device(
         CUDA_TRY(&turtle_stepper_trace_batch_device, cudaSetDevice(plan->device));
         memset(&plan->counters, 0x0, sizeof(plan->counters));
         plan->counters.rays = n;
+        const int slot = next_device_slot(plan);
+        const DeviceIo io = { position, direction, NULL, results, NULL };
         CUDA_TRY(&turtle_stepper_trace_batch_device,
-            launch_trace(plan, N_SLOTS, n, position, direction, rule, results,
-                plan->d_counters + 4 * N_SLOTS, (cudaStream_t)stream));
+            launch_trace(plan, slot, n, io, rule, plan->d_counters + CTR * slot,
+                (cudaStream_t)stream));
         return TURTLE_RETURN_SUCCESS;
 }
 
@@ -1926,9 +2154,11 @@ extern "C" enum turtle_return turtle_stepper_trace_crossings_device(
         CUDA_TRY(fn, cudaSetDevice(plan->device));
         memset(&plan->counters, 0x0, sizeof(plan->counters));
         plan->counters.rays = n;
-        CUDA_TRY(fn, launch_trace(plan, N_SLOTS, n, position, direction, rule, results,
-                         plan->d_counters + 4 * N_SLOTS, (cudaStream_t)stream, NULL,
-                         (max_crossings > 0) ? crossings : NULL, max_crossings));
+        const int slot = next_device_slot(plan);
+        const DeviceIo io = { position, direction, NULL, results, NULL };
+        CUDA_TRY(fn, launch_trace(plan, slot, n, io, rule, plan->d_counters + CTR * slot,
+                         (cudaStream_t)stream, NULL, (max_crossings > 0) ? crossings : NULL,
+                         max_crossings));
         return TURTLE_RETURN_SUCCESS;
 }
 
@@ -1965,45 +2195,167 @@ static cudaError_t plan_pipeline(struct turtle_plan * plan, size_t rays)
 extern "C" void turtle_plan_counters_sync(struct turtle_plan * plan)
 {
         /* device-pointer calls: the caller has synchronised its stream */
-        unsigned long long c[4];
+        unsigned long long c[CTR];
         cudaSetDevice(plan->device);
-        if (cudaMemcpy(c, plan->d_counters + 4 * N_SLOTS, sizeof c, cudaMemcpyDeviceToHost) ==
-            cudaSuccess) {
+        if (cudaMemcpy(c, plan->d_counters + CTR * plan->dev_slot, sizeof c,
+                cudaMemcpyDeviceToHost) == cudaSuccess) {
                 plan->counters.steps = c[1];
                 plan->counters.samples = c[2];
+                plan->counters.rebuilds = c[4];
         }
+}
+
+/* ---- fans and field arrays ------------------------------------------------------------- */
+
+static enum turtle_return check_fan(turtle_function_t * fn, const struct turtle_fan * fan,
+    size_t * n, size_t * bundle)
+{
+        if ((fan == NULL) || ((fan->n_azimuth > 0) && (fan->azimuth == NULL)) ||
+            ((fan->n_elevation > 0) && (fan->elevation == NULL)))
+                return tbh::raise(fn, TURTLE_RETURN_BAD_ADDRESS, BATCH_CU, __LINE__,
+                    "missing fan angles");
+        *bundle = (fan->bundle > 0) ? fan->bundle : 1;
+        if ((fan->n_elevation % *bundle) != 0)
+                return tbh::raise(fn, TURTLE_RETURN_DOMAIN_ERROR, BATCH_CU, __LINE__,
+                    "the number of elevations of a fan (%zu) must be a multiple of its bundle (%zu)",
+                    fan->n_elevation, *bundle);
+        *n = fan->n_azimuth * fan->n_elevation;
+        return TURTLE_RETURN_SUCCESS;
+}
+
+/* Sines and cosines of the angles of a fan, taken on the host by the calls of
+ * turtle_ecef_from_horizontal (ecef.c:139-144,170-173), and the East / North / Up frame of
+ * its station (compute_enu, ecef.c:136-158); queued for upload on `stream`. */
+static cudaError_t fan_upload(struct turtle_plan * plan, int slot, const struct turtle_fan * fan,
+    size_t bundle, size_t ray0, cudaStream_t stream, FanTables * T)
+{
+        const size_t angles = fan->n_azimuth + fan->n_elevation;
+        if (plan->fan_angles[slot] < angles) {
+                if (plan->h_fan[slot] != NULL) cudaFreeHost(plan->h_fan[slot]);
+                cudaFree(plan->d_fan[slot]);
+                plan->h_fan[slot] = NULL;
+                plan->d_fan[slot] = NULL;
+                plan->fan_angles[slot] = 0;
+                cudaError_t err = cudaHostAlloc((void **)&plan->h_fan[slot], angles * sizeof(double2),
+                    cudaHostAllocDefault);
+                if (err == cudaSuccess)
+                        err = cudaMalloc((void **)&plan->d_fan[slot], angles * sizeof(double2));
+                if (err != cudaSuccess) return err;
+                plan->fan_angles[slot] = angles;
+        }
+        double2 * h = plan->h_fan[slot];
+        for (size_t i = 0; i < fan->n_azimuth; i++) {
+                const double az = fan->azimuth[i] * M_PI / 180.;
+                h[i].x = sin(az);
+                h[i].y = cos(az);
+        }
+        for (size_t j = 0; j < fan->n_elevation; j++) {
+                const double el = fan->elevation[j] * M_PI / 180.;
+                h[fan->n_azimuth + j].x = cos(el);
+                h[fan->n_azimuth + j].y = sin(el);
+        }
+        const double lambda = fan->longitude * M_PI / 180.;
+        const double phi = fan->latitude * M_PI / 180.;
+        const double sl = sin(lambda), cl = cos(lambda), sp = sin(phi), cp = cos(phi);
+        const double e[3] = { -sl, cl, 0. }, nn[3] = { -cl * sp, -sl * sp, cp };
+        const double u[3] = { cl * cp, sl * cp, sp };
+        for (int c = 0; c < 3; c++) {
+                T->origin[c] = fan->position[c];
+                T->e[c] = e[c];
+                T->n[c] = nn[c];
+                T->u[c] = u[c];
+        }
+        T->az = plan->d_fan[slot];
+        T->el = plan->d_fan[slot] + fan->n_azimuth;
+        T->naz = fan->n_azimuth;
+        T->bundle = bundle;
+        T->ray0 = ray0;
+        return cudaMemcpyAsync(plan->d_fan[slot], h, angles * sizeof(double2),
+            cudaMemcpyHostToDevice, stream);
+}
+
+/* The field arrays of a call, one after the other: (pointer slot, bytes per ray). */
+struct FieldSpec {
+        void * const * host; /* where the caller's pointer sits in its turtle_trace_fields */
+        size_t offset;       /* ... as a byte offset, to address the device copy alike */
+        size_t bytes;        /* per ray */
+};
+
+static int field_specs(const struct turtle_trace_fields * f, FieldSpec specs[12])
+{
+        int k = 0;
+#define FIELD(member, size)                                                          \
+        if (f->member != NULL) {                                                     \
+                specs[k].host = (void * const *)&f->member;                          \
+                specs[k].offset = (size_t)((const char *)&f->member - (const char *)f); \
+                specs[k].bytes = (size);                                             \
+                k++;                                                                 \
+        }
+        FIELD(length[0], 8) FIELD(length[1], 8) FIELD(length[2], 8) FIELD(length[3], 8)
+        FIELD(total, 8) FIELD(altitude, 8) FIELD(position, 24) FIELD(n_steps, 4)
+        FIELD(status, 4) FIELD(index, 8) FIELD(medium_hash, 4) FIELD(n_changes, 4)
+#undef FIELD
+        return k;
 }
 
 /* Host-pointer call, streamed: ONE persistent trace kernel over all the rays while the
  * copy engines feed and drain it.
  *   stream 1 (H2D): for each chunk, positions and directions, then the new watermark
- *                   (an 8-byte copy, ordered after the data of the chunk);
+ *                   (an 8-byte copy, ordered after the data of the chunk) -- a fan has no
+ *                   rays to copy: its tables go first and the watermark is raised at once;
  *   stream 0      : the trace kernel -- a lane that holds ticket q waits until the
  *                   watermark has passed q (MODE_WAIT), and every finished ray is counted
  *                   for its chunk after a __threadfence;
  *   drain streams : the lane that counts the last ray of a chunk raises the chunk's flag in
  *                   mapped host memory; the calling thread watches the flags and queues the
- *                   copy of each chunk's records as it completes.
+ *                   copy of each chunk's records and / or field slices as it completes.
  * Compared with one kernel per chunk there is a single kernel tail instead of one per
  * chunk, and no lane ever idles between chunks. */
-static enum turtle_return trace_streamed(struct turtle_plan * plan, size_t n,
-    const double * position, const double * direction, const struct turtle_trace_rule * rule,
-    struct turtle_trace_result * results, int chunk_shift)
+static enum turtle_return trace_streamed(turtle_function_t * fn, struct turtle_plan * plan,
+    size_t n, size_t ray0, const double * position, const double * direction,
+    const struct turtle_fan * fan, size_t bundle, const struct turtle_trace_rule * rule,
+    struct turtle_trace_result * results, const struct turtle_trace_fields * fields,
+    int chunk_shift)
 {
-        turtle_function_t * fn = FN(&turtle_stepper_trace_batch);
         const size_t chunk = (size_t)1 << chunk_shift;
         const size_t n_chunks = (n + chunk - 1) / chunk;
         CUDA_TRY(fn, plan_pipeline(plan, 1)); /* the three streams and their events */
         if (plan->ev_reset == NULL) CUDA_TRY(fn, cudaEventCreate(&plan->ev_reset));
-        if (plan->all_rays < n) {
+        if ((fan == NULL) && (plan->all_rays < n)) {
                 cudaFree(plan->d_all_in);
-                cudaFree(plan->d_all_out);
                 plan->d_all_in = NULL;
-                plan->d_all_out = NULL;
                 plan->all_rays = 0;
                 CUDA_TRY(fn, cudaMalloc((void **)&plan->d_all_in, (n * 6 + 32) * sizeof(double)));
-                CUDA_TRY(fn, cudaMalloc((void **)&plan->d_all_out, n * sizeof(turtle_trace_result)));
                 plan->all_rays = n;
+        }
+        if ((results != NULL) && (plan->all_records < n)) {
+                cudaFree(plan->d_all_out);
+                plan->d_all_out = NULL;
+                plan->all_records = 0;
+                CUDA_TRY(fn, cudaMalloc((void **)&plan->d_all_out, n * sizeof(turtle_trace_result)));
+                plan->all_records = n;
+        }
+        /* device copies of the field arrays the caller asked for */
+        FieldSpec specs[12];
+        const int n_fields = (fields != NULL) ? field_specs(fields, specs) : 0;
+        struct turtle_trace_fields d_fields;
+        memset(&d_fields, 0x0, sizeof d_fields);
+        if (n_fields > 0) {
+                size_t need = 0;
+                for (int k = 0; k < n_fields; k++) need += (n * specs[k].bytes + 255) / 256 * 256;
+                if (plan->field_pool_bytes < need) {
+                        cudaFree(plan->d_field_pool);
+                        plan->d_field_pool = NULL;
+                        plan->field_pool_bytes = 0;
+                        CUDA_TRY(fn, cudaMalloc(&plan->d_field_pool, need));
+                        plan->field_pool_bytes = need;
+                }
+                size_t at = 0;
+                for (int k = 0; k < n_fields; k++) {
+                        *(void **)((char *)&d_fields + specs[k].offset) =
+                            (char *)plan->d_field_pool + at;
+                        at += (n * specs[k].bytes + 255) / 256 * 256;
+                }
         }
         if (plan->stream_chunks < n_chunks) {
                 cudaFree(plan->d_stream_state);
@@ -2025,11 +2377,11 @@ static enum turtle_return trace_streamed(struct turtle_plan * plan, size_t n,
         for (int j = 0; j < N_DRAINS; j++)
                 if (plan->drain[j] == NULL)
                         CUDA_TRY(fn, cudaStreamCreateWithFlags(&plan->drain[j], cudaStreamNonBlocking));
-        unsigned long long * d_counters = plan->d_counters + 4 * 0;
+        unsigned long long * d_counters = plan->d_counters + CTR * 0;
         /* both arrays start on a 256-byte boundary and a chunk is a multiple of 128 bytes:
          * no cache line holds rays of two chunks */
         double * d_pos = plan->d_all_in;
-        double * d_dir = plan->d_all_in + (3 * n + 31) / 32 * 32;
+        double * d_dir = (plan->d_all_in != NULL) ? plan->d_all_in + (3 * n + 31) / 32 * 32 : NULL;
         StreamState st;
         st.chunk_shift = chunk_shift;
         st.watermark = plan->d_stream_state;
@@ -2046,7 +2398,15 @@ static enum turtle_return trace_streamed(struct turtle_plan * plan, size_t n,
         CUDA_TRY(fn, cudaStreamWaitEvent(h2d, plan->ev_reset, 0));
         plan->counters.launches = 0;
         cudaError_t err = cudaSuccess;
-        for (size_t k = 0; (k < n_chunks) && (err == cudaSuccess); k++) {
+        FanTables tables;
+        if (fan != NULL) {
+                err = fan_upload(plan, 0, fan, bundle, ray0, h2d, &tables);
+                plan->h_marks[0] = n;
+                if (err == cudaSuccess)
+                        err = cudaMemcpyAsync(plan->d_stream_state, &plan->h_marks[0],
+                            sizeof(unsigned long long), cudaMemcpyHostToDevice, h2d);
+        }
+        for (size_t k = 0; (fan == NULL) && (k < n_chunks) && (err == cudaSuccess); k++) {
                 const size_t i0 = k * chunk;
                 const size_t m = std::min(chunk, n - i0);
                 plan->h_marks[k] = i0 + m;
@@ -2065,8 +2425,10 @@ static enum turtle_return trace_streamed(struct turtle_plan * plan, size_t n,
                     "CUDA error in the streamed trace: %s", cudaGetErrorString(err));
         }
         CUDA_TRY(fn, cudaEventRecord(plan->ev0[0], compute));
-        err = launch_trace(plan, 0, n, d_pos, d_dir, rule, plan->d_all_out, d_counters, compute,
-            &st);
+        const DeviceIo io = { (fan == NULL) ? d_pos : NULL, (fan == NULL) ? d_dir : NULL,
+                (fan != NULL) ? &tables : NULL, (results != NULL) ? plan->d_all_out : NULL,
+                (n_fields > 0) ? &d_fields : NULL };
+        err = launch_trace(plan, 0, n, io, rule, d_counters, compute, &st);
         if (err == cudaSuccess) err = cudaEventRecord(plan->ev1[0], compute);
         /* Drain the chunks in the order they COMPLETE (a chunk waits for its longest ray:
          * the first chunks of a fan sorted longest-first complete late): the thread that
@@ -2083,9 +2445,14 @@ static enum turtle_return trace_streamed(struct turtle_plan * plan, size_t n,
                                 continue;
                         const size_t i0 = k * chunk;
                         const size_t m = std::min(chunk, n - i0);
-                        err = cudaMemcpyAsync(results + i0, plan->d_all_out + i0,
-                            m * sizeof(turtle_trace_result), cudaMemcpyDeviceToHost,
-                            plan->drain[(n_chunks - remaining) % N_DRAINS]);
+                        cudaStream_t out = plan->drain[(n_chunks - remaining) % N_DRAINS];
+                        if (results != NULL)
+                                err = cudaMemcpyAsync(results + i0, plan->d_all_out + i0,
+                                    m * sizeof(turtle_trace_result), cudaMemcpyDeviceToHost, out);
+                        for (int f = 0; (f < n_fields) && (err == cudaSuccess); f++)
+                                err = cudaMemcpyAsync((char *)*specs[f].host + i0 * specs[f].bytes,
+                                    *(char **)((char *)&d_fields + specs[f].offset) + i0 * specs[f].bytes,
+                                    m * specs[f].bytes, cudaMemcpyDeviceToHost, out);
                         drained[k] = 1;
                         remaining--;
                         progress = true;
@@ -2114,16 +2481,129 @@ static enum turtle_return trace_streamed(struct turtle_plan * plan, size_t n,
         for (int j = 0; j < N_DRAINS; j++) CUDA_TRY(fn, cudaStreamSynchronize(plan->drain[j]));
         float ms = 0.f;
         cudaEventElapsedTime(&ms, plan->ev0[0], plan->ev1[0]);
-        unsigned long long c4[4];
+        unsigned long long c4[CTR];
         CUDA_TRY(fn, cudaMemcpy(c4, d_counters, sizeof c4, cudaMemcpyDeviceToHost));
         plan->counters.rays = n;
         plan->counters.steps = c4[1];
         plan->counters.samples = c4[2];
+        plan->counters.rebuilds = c4[4];
         plan->counters.kernel_ms = ms;
         plan->counters.launches += 1;
         if (c4[3] != 0ull)
                 return tbh::raise(fn, TURTLE_RETURN_LIBRARY_ERROR, BATCH_CU, __LINE__,
                     "the streamed trace timed out waiting for its rays to reach the device");
+        return TURTLE_RETURN_SUCCESS;
+}
+
+/* A host-pointer call in rounds of at most STREAM_MAX_RAYS rays, which bounds the device
+ * staging of a call whatever the size of the batch. */
+static enum turtle_return trace_rounds(turtle_function_t * fn, struct turtle_plan * plan,
+    size_t n, const double * position, const double * direction, const struct turtle_fan * fan,
+    size_t bundle, const struct turtle_trace_rule * rule, struct turtle_trace_result * results,
+    const struct turtle_trace_fields * fields)
+{
+        turtle_plan_counters sum;
+        memset(&sum, 0x0, sizeof(sum));
+        size_t round_rays = STREAM_MAX_RAYS;
+        if (getenv("TURTLE_B200_STREAM_MAX_RAYS") != NULL) { /* tests: small rounds */
+                const long long v = atoll(getenv("TURTLE_B200_STREAM_MAX_RAYS"));
+                if (v >= (long long)STREAM_CHUNK_RAYS) round_rays = (size_t)v;
+        }
+        FieldSpec specs[12];
+        const int n_fields = (fields != NULL) ? field_specs(fields, specs) : 0;
+        for (size_t first = 0; first < n; first += round_rays) {
+                const size_t m = std::min(round_rays, n - first);
+                struct turtle_trace_fields part;
+                memset(&part, 0x0, sizeof part);
+                for (int k = 0; k < n_fields; k++)
+                        *(void **)((char *)&part + specs[k].offset) =
+                            (char *)*specs[k].host + first * specs[k].bytes;
+                const enum turtle_return rc = trace_streamed(fn, plan, m, first,
+                    (position != NULL) ? position + 3 * first : NULL,
+                    (direction != NULL) ? direction + 3 * first : NULL, fan, bundle, rule,
+                    (results != NULL) ? results + first : NULL, (n_fields > 0) ? &part : NULL,
+                    STREAM_CHUNK_SHIFT);
+                if (rc != TURTLE_RETURN_SUCCESS) return rc;
+                sum.rays += plan->counters.rays;
+                sum.steps += plan->counters.steps;
+                sum.samples += plan->counters.samples;
+                sum.rebuilds += plan->counters.rebuilds;
+                sum.launches += plan->counters.launches;
+                sum.kernel_ms += plan->counters.kernel_ms;
+        }
+        plan->counters = sum;
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_stepper_trace_fan(struct turtle_plan * plan,
+    const struct turtle_fan * fan, const struct turtle_trace_rule * rule,
+    struct turtle_trace_result * results, const struct turtle_trace_fields * fields)
+{
+        turtle_function_t * fn = FN(&turtle_stepper_trace_fan);
+        enum turtle_return rc = check_rule(fn, rule);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        size_t n, bundle;
+        rc = check_fan(fn, fan, &n, &bundle);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        memset(&plan->counters, 0x0, sizeof(plan->counters));
+        if (n == 0) return TURTLE_RETURN_SUCCESS;
+        CUDA_TRY(fn, cudaSetDevice(plan->device));
+        return trace_rounds(fn, plan, n, NULL, NULL, fan, bundle, rule, results, fields);
+}
+
+extern "C" enum turtle_return turtle_stepper_trace_fan_device(struct turtle_plan * plan,
+    const struct turtle_fan * fan, const struct turtle_trace_rule * rule,
+    struct turtle_trace_result * results, const struct turtle_trace_fields * fields,
+    void * stream)
+{
+        turtle_function_t * fn = FN(&turtle_stepper_trace_fan_device);
+        enum turtle_return rc = check_rule(fn, rule);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        size_t n, bundle;
+        rc = check_fan(fn, fan, &n, &bundle);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        if (n == 0) return TURTLE_RETURN_SUCCESS;
+        CUDA_TRY(fn, cudaSetDevice(plan->device));
+        memset(&plan->counters, 0x0, sizeof(plan->counters));
+        plan->counters.rays = n;
+        const int slot = next_device_slot(plan);
+        FanTables tables;
+        CUDA_TRY(fn, fan_upload(plan, slot, fan, bundle, 0, (cudaStream_t)stream, &tables));
+        const DeviceIo io = { NULL, NULL, &tables, results, fields };
+        CUDA_TRY(fn, launch_trace(plan, slot, n, io, rule, plan->d_counters + CTR * slot,
+                         (cudaStream_t)stream));
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_stepper_trace_fields(struct turtle_plan * plan, size_t n,
+    const double * position, const double * direction, const struct turtle_trace_rule * rule,
+    const struct turtle_trace_fields * fields)
+{
+        turtle_function_t * fn = FN(&turtle_stepper_trace_fields);
+        enum turtle_return rc = check_rule(fn, rule);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        memset(&plan->counters, 0x0, sizeof(plan->counters));
+        if (n == 0) return TURTLE_RETURN_SUCCESS;
+        CUDA_TRY(fn, cudaSetDevice(plan->device));
+        return trace_rounds(fn, plan, n, position, direction, NULL, 1, rule, NULL, fields);
+}
+
+extern "C" enum turtle_return turtle_stepper_trace_fields_device(struct turtle_plan * plan,
+    size_t n, const double * position, const double * direction,
+    const struct turtle_trace_rule * rule, const struct turtle_trace_fields * fields,
+    void * stream)
+{
+        turtle_function_t * fn = FN(&turtle_stepper_trace_fields_device);
+        enum turtle_return rc = check_rule(fn, rule);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        if (n == 0) return TURTLE_RETURN_SUCCESS;
+        CUDA_TRY(fn, cudaSetDevice(plan->device));
+        memset(&plan->counters, 0x0, sizeof(plan->counters));
+        plan->counters.rays = n;
+        const int slot = next_device_slot(plan);
+        const DeviceIo io = { position, direction, NULL, NULL, fields };
+        CUDA_TRY(fn, launch_trace(plan, slot, n, io, rule, plan->d_counters + CTR * slot,
+                         (cudaStream_t)stream));
         return TURTLE_RETURN_SUCCESS;
 }
 
@@ -2140,28 +2620,9 @@ extern "C" enum turtle_return turtle_stepper_trace_batch(
         /* more than one chunk, caller's ray order: stream the batch through one kernel --
          * in rounds of at most STREAM_MAX_RAYS rays, which bounds the device staging of a
          * call (144 bytes per ray) to 4.6 GB whatever the size of the batch */
-        if ((plan->schedule == 0) && (plan->pipeline_mode != 1) && (n > STREAM_CHUNK_RAYS)) {
-                turtle_plan_counters sum;
-                memset(&sum, 0x0, sizeof(sum));
-                size_t round_rays = STREAM_MAX_RAYS;
-                if (getenv("TURTLE_B200_STREAM_MAX_RAYS") != NULL) { /* tests: small rounds */
-                        const long long v = atoll(getenv("TURTLE_B200_STREAM_MAX_RAYS"));
-                        if (v >= (long long)STREAM_CHUNK_RAYS) round_rays = (size_t)v;
-                }
-                for (size_t first = 0; first < n; first += round_rays) {
-                        const size_t m = std::min(round_rays, n - first);
-                        rc = trace_streamed(plan, m, position + 3 * first, direction + 3 * first,
-                            rule, results + first, STREAM_CHUNK_SHIFT);
-                        if (rc != TURTLE_RETURN_SUCCESS) return rc;
-                        sum.rays += plan->counters.rays;
-                        sum.steps += plan->counters.steps;
-                        sum.samples += plan->counters.samples;
-                        sum.launches += plan->counters.launches;
-                        sum.kernel_ms += plan->counters.kernel_ms;
-                }
-                plan->counters = sum;
-                return TURTLE_RETURN_SUCCESS;
-        }
+        if ((plan->schedule == 0) && (plan->pipeline_mode != 1) && (n > STREAM_CHUNK_RAYS))
+                return trace_rounds(FN(&turtle_stepper_trace_batch), plan, n, position, direction,
+                    NULL, 1, rule, results, NULL);
         size_t chunk_rays = CHUNK_RAYS;
         if (getenv("TURTLE_B200_CHUNK_RAYS") != NULL) { /* development: pipeline sweep */
                 const long long v = atoll(getenv("TURTLE_B200_CHUNK_RAYS"));
@@ -2172,9 +2633,9 @@ extern "C" enum turtle_return turtle_stepper_trace_batch(
 
         /* chunked 3-deep pipeline: H2D(c+1) | kernel(c) | D2H(c-1) on 3 streams */
         const size_t n_chunks = (n + chunk - 1) / chunk;
-        std::vector<unsigned long long> totals(4, 0ull);
+        std::vector<unsigned long long> totals(CTR, 0ull);
         double kernel_ms = 0.;
-        unsigned long long c4[4];
+        unsigned long long c4[CTR];
         for (size_t c = 0; c < n_chunks + N_SLOTS; c++) {
                 const int s = (int)(c % N_SLOTS);
                 if (c >= N_SLOTS) { /* drain the slot before reusing it */
@@ -2183,10 +2644,11 @@ extern "C" enum turtle_return turtle_stepper_trace_batch(
                         cudaEventElapsedTime(&ms, plan->ev0[s], plan->ev1[s]);
                         kernel_ms += ms;
                         CUDA_TRY(&turtle_stepper_trace_batch,
-                            cudaMemcpy(c4, plan->d_counters + 4 * s, sizeof c4,
+                            cudaMemcpy(c4, plan->d_counters + CTR * s, sizeof c4,
                                 cudaMemcpyDeviceToHost));
                         totals[1] += c4[1];
                         totals[2] += c4[2];
+                        totals[4] += c4[4];
                 }
                 if (c >= n_chunks) continue;
                 const size_t i0 = c * chunk;
@@ -2201,9 +2663,9 @@ extern "C" enum turtle_return turtle_stepper_trace_batch(
                     cudaMemcpyAsync(d_dir, direction + 3 * i0, m * 3 * sizeof(double),
                         cudaMemcpyHostToDevice, st));
                 CUDA_TRY(&turtle_stepper_trace_batch, cudaEventRecord(plan->ev0[s], st));
+                const DeviceIo io = { d_pos, d_dir, NULL, plan->d_out[s], NULL };
                 CUDA_TRY(&turtle_stepper_trace_batch,
-                    launch_trace(plan, s, m, d_pos, d_dir, rule, plan->d_out[s],
-                        plan->d_counters + 4 * s, st));
+                    launch_trace(plan, s, m, io, rule, plan->d_counters + CTR * s, st));
                 CUDA_TRY(&turtle_stepper_trace_batch, cudaEventRecord(plan->ev1[s], st));
                 CUDA_TRY(&turtle_stepper_trace_batch,
                     cudaMemcpyAsync(results + i0, plan->d_out[s],
@@ -2212,6 +2674,7 @@ extern "C" enum turtle_return turtle_stepper_trace_batch(
         plan->counters.rays = n;
         plan->counters.steps = totals[1];
         plan->counters.samples = totals[2];
+        plan->counters.rebuilds = totals[4];
         plan->counters.kernel_ms = kernel_ms;
         return TURTLE_RETURN_SUCCESS;
 }
@@ -2231,14 +2694,9 @@ extern "C" enum turtle_return turtle_states_create(
         states->n = n;
         states->d_states = NULL;
         states->stride = (std::max<size_t>(n, 1) + 31) / 32 * 32;
-        states->n_transforms = plan->G.n_transforms;
-        states->d_lla = NULL;
+        const size_t rows = PS_FIELDS + ((plan->G.range > 0.) ? plan->G.lla_rows : 0);
         cudaError_t err = cudaMalloc((void **)&states->d_states,
-            states->stride * PS_FIELDS * sizeof(double));
-        if (err == cudaSuccess)
-                err = cudaMalloc((void **)&states->d_lla, std::max<size_t>(n, 1) *
-                        std::max(states->n_transforms, 1) * sizeof(tb::LlaState));
-        if (err != cudaSuccess) cudaFree(states->d_states);
+            states->stride * rows * sizeof(double));
         if (err != cudaSuccess) {
                 delete states;
                 return tbh::raise(FN(&turtle_states_create), TURTLE_RETURN_MEMORY_ERROR,
@@ -2254,9 +2712,14 @@ extern "C" void turtle_states_destroy(struct turtle_states ** states)
         if ((states == NULL) || (*states == NULL)) return;
         cudaSetDevice((*states)->plan->device);
         cudaFree((*states)->d_states);
-        cudaFree((*states)->d_lla);
         delete *states;
         *states = NULL;
+}
+
+extern "C" size_t turtle_states_bytes_per_particle(const struct turtle_states * states)
+{
+        const tb::Geometry & G = states->plan->G;
+        return (PS_FIELDS + ((G.range > 0.) ? G.lla_rows : 0)) * sizeof(double);
 }
 
 extern "C" enum turtle_return turtle_states_reset(struct turtle_states * states)
@@ -2265,8 +2728,9 @@ extern "C" enum turtle_return turtle_states_reset(struct turtle_states * states)
         if (states->n == 0) return TURTLE_RETURN_SUCCESS;
         const int blocks = (int)std::min<size_t>((states->n + 255) / 256,
             (size_t)states->plan->sm_count * 8);
-        states_reset_kernel<<<blocks, 256>>>(states->d_states, states->d_lla, states->stride,
-            states->n, states->n_transforms);
+        tb::Geometry G = states->plan->G;
+        if (!(G.range > 0.)) G.n_transforms = 0; /* no local approximation rows */
+        states_reset_kernel<<<blocks, 256>>>(G, states->d_states, states->stride, states->n);
         states->plan->counters.launches++;
         CUDA_TRY(&turtle_states_reset, cudaGetLastError());
         CUDA_TRY(&turtle_states_reset, cudaDeviceSynchronize());
@@ -2288,7 +2752,6 @@ extern "C" enum turtle_return turtle_stepper_step_batch_device(
         StepArgs A;
         A.n = n;
         A.states = (states != NULL) ? states->d_states : NULL;
-        A.lla_states = (states != NULL) ? states->d_lla : NULL;
         A.stride = (states != NULL) ? states->stride : 0;
         A.position = position;
         A.direction = direction;
@@ -2298,13 +2761,13 @@ extern "C" enum turtle_return turtle_stepper_step_batch_device(
         A.elevation = elevation;
         A.step = step;
         A.index = index;
-        A.counters = plan->d_counters + 4 * N_SLOTS;
+        A.counters = plan->d_counters + CTR * next_device_slot(plan);
         const int threads = 128;
-        const int blocks = (int)std::min<size_t>((n + threads - 1) / threads,
+        int blocks = (int)std::min<size_t>((n + threads - 1) / threads,
             (size_t)plan->sm_count * 5);
         cudaStream_t st = (cudaStream_t)stream;
         CUDA_TRY(&turtle_stepper_step_batch_device,
-            cudaMemsetAsync(A.counters, 0x0, 4 * sizeof(unsigned long long), st));
+            cudaMemsetAsync(A.counters, 0x0, CTR * sizeof(unsigned long long), st));
         const bool lla = plan->G.range > 0.;
         bool proj = false;
         for (int t = 0; t < plan->G.n_transforms; t++)
@@ -2315,15 +2778,25 @@ extern "C" enum turtle_return turtle_stepper_step_batch_device(
             (lla && proj) ? walk_kernel<true, true> :
             (lla ? walk_kernel<true, false> :
                    (proj ? walk_kernel<false, true> : walk_kernel<false, false>));
+        /* the local approximations live in the device states, else (no states: every
+         * particle starts from a reset stepper) in dynamic shared memory */
+        const size_t dynamic = (lla && (states == NULL)) ? lla_bytes(plan) : 0;
         cudaFuncAttributes attr;
         if (cudaFuncGetAttributes(&attr, kernel) == cudaSuccess) {
-                const size_t need = 5 * (attr.sharedSizeBytes + 1024);
-                int percent = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+                const size_t cta = attr.sharedSizeBytes + dynamic + 1024;
+                int per_sm = (int)((227 * 1024) / cta);
+                if (per_sm > 5) per_sm = 5;
+                if (per_sm < 1) per_sm = 1;
+                blocks = (int)std::min<size_t>((size_t)blocks, (size_t)plan->sm_count * per_sm);
+                int percent = (int)((per_sm * cta * 100 + 228 * 1024 - 1) / (228 * 1024));
                 if (percent > 100) percent = 100;
                 cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
         }
+        if (dynamic > 0)
+                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                    (int)dynamic);
         cudaGetLastError();
-        kernel<<<blocks, threads, 0, st>>>(plan->G, A);
+        kernel<<<blocks, threads, dynamic, st>>>(plan->G, A);
         plan->counters.launches++;
         plan->counters.rays = n;
         plan->counters.steps = (direction != NULL) ? n : 0;
@@ -2940,6 +3413,37 @@ extern "C" double turtle_b200_dfma_peak(int repeats)
         return best;
 }
 
+/* Registers and static shared memory of a built kernel, by role (turtle_b200.h). */
+extern "C" int turtle_b200_kernel_info(const char * name, int * registers, int * shared_bytes)
+{
+        const void * f = NULL;
+#define ROLE(role, kernel) \
+        if (strcmp(name, role) == 0) f = (const void *)(kernel)
+        ROLE("trace_stack", (trace_kernel<false, false, 6, tb::SHAPE_STACK, false>));
+        ROLE("trace_stack_stream", (trace_kernel<false, false, 6, tb::SHAPE_STACK, true>));
+        ROLE("trace", (trace_kernel<false, false, 6, tb::SHAPE_GENERIC, false>));
+        ROLE("trace_proj", (trace_kernel<false, true, 6, tb::SHAPE_GENERIC, false>));
+        ROLE("trace_lla", (trace_kernel<true, false, 4, tb::SHAPE_GENERIC, false>));
+        ROLE("trace_lla_proj", (trace_kernel<true, true, 4, tb::SHAPE_GENERIC, false>));
+        ROLE("walk", (walk_kernel<false, false>));
+        ROLE("walk_proj", (walk_kernel<false, true>));
+        ROLE("walk_lla", (walk_kernel<true, false>));
+        ROLE("walk_lla_proj", (walk_kernel<true, true>));
+        ROLE("to_geodetic", to_geodetic_kernel);
+        ROLE("map_elevation", map_elevation_kernel);
+        ROLE("map_elevation_ecef", map_elevation_ecef_kernel);
+#undef ROLE
+        if (f == NULL) return -1;
+        cudaFuncAttributes attr;
+        if (cudaFuncGetAttributes(&attr, f) != cudaSuccess) {
+                cudaGetLastError();
+                return -2;
+        }
+        if (registers != NULL) *registers = attr.numRegs;
+        if (shared_bytes != NULL) *shared_bytes = (int)attr.sharedSizeBytes;
+        return 0;
+}
+
 /* Names of the batched entry points, for the error message format. */
 extern "C" const char * tb_batch_function_name(turtle_function_t * caller)
 {
@@ -2972,6 +3476,10 @@ extern "C" const char * tb_batch_function_name(turtle_function_t * caller)
         NAME(turtle_stepper_freeze_region);
         NAME(turtle_map_resample);
         NAME(turtle_residency_from_rays);
+        NAME(turtle_stepper_trace_fan);
+        NAME(turtle_stepper_trace_fan_device);
+        NAME(turtle_stepper_trace_fields);
+        NAME(turtle_stepper_trace_fields_device);
         NAME(turtle_stepper_trace_crossings);
         NAME(turtle_stepper_trace_crossings_device);
         NAME(turtle_b200_peer_alloc);
