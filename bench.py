@@ -214,7 +214,7 @@ def workload_config(n_rays, gpus):
                   "no explicit flush" % (n_rays * BYTES_PER_RAY / 1e6)}
 
 
-def kernel_profile(role):
+def kernel_profile(name):
     """The committed ncu measurement of a kernel (profiles/r02_kernels.json, written by
     tools/kernel_profiles.py from the .ncu-rep captures): executed FP64-pipe lane slots
     per sample and DRAM bytes of the captured launch. Refused -- so that a stale number
@@ -223,14 +223,14 @@ def kernel_profile(role):
     path = os.path.join(ROOT, "profiles", "r02_kernels.json")
     if not os.path.exists(path):
         return None, "profiles/r02_kernels.json is missing"
-    entry = json.load(open(path)).get(role)
+    entry = json.load(open(path)).get(name)
     if entry is None:
-        return None, "no entry `%s' in profiles/r02_kernels.json" % role
+        return None, "no entry `%s' in profiles/r02_kernels.json" % name
     import turtle_b200 as tb
-    info = tb.kernel_info(role)
+    info = tb.kernel_info(entry["role"])
     if info is None or info[0] != entry["registers"]:
-        return None, "profile of `%s' is stale: captured at %s registers, built kernel has %s" % (
-            role, entry["registers"], info[0] if info else None)
+        return None, "profile `%s' is stale: captured at %s registers, the built %s has %s" % (
+            name, entry["registers"], entry["role"], info[0] if info else None)
     return entry, "profiles/%s" % entry.get("source", "r02_kernels.json")
 
 
@@ -506,7 +506,7 @@ def main():
         hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
     dfma = tb.dfma_peak(3)  # G FP64-pipe instructions / s, measured now on this GPU
     samples, steps = counters["samples"], counters["steps"]
-    prof, prof_src = kernel_profile("trace_stack")
+    prof, prof_src = kernel_profile("c2_trace_stack")
     ops = prof["fp64_lane_slots_per_sample"] if prof else None
     achieved_ops = ops * samples / (kernel_ms * 1e-3) / 1e12 if prof else None
     alg_bytes = n * BYTES_PER_RAY + samples * BYTES_PER_SAMPLE

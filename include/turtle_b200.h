@@ -92,6 +92,7 @@ struct turtle_plan_counters {
         double kernel_ms;  /* device time of the kernels (CUDA events), host-pointer calls only */
         uint64_t rebuilds; /* local approximation: Jacobian columns evaluated (one ECEF ->
                             * geodetic transform each, like a sample) */
+        uint64_t window_hits; /* gather mode 2: samples whose nodes came from shared memory */
 };
 
 /* ---- plans ---------------------------------------------------------------- */
@@ -174,6 +175,20 @@ TURTLE_API void turtle_plan_specialise_set(struct turtle_plan * plan, int enable
  * chunks are copied back as they complete). 1: chunked -- one kernel per 1 Mi-ray chunk on
  * three streams (also used whenever a ray schedule is set). Results are identical. */
 TURTLE_API void turtle_plan_pipeline_set(struct turtle_plan * plan, int mode);
+
+/* How the trace kernel of a single uniform stack (the muography case) gathers the four
+ * nodes of a sample (ref: the 2 x 2 gather of turtle_map_elevation_, map.c:266-271).
+ *   0  four 16-bit loads from the row-major tiles (default);
+ *   1  one 8-byte load from a CELL-PACKED second copy of the tiles, built here on the
+ *      device: 4 x the tile bytes of HBM for one request and one sector per sample;
+ *   2  a 64 x 64-node window of the tile under (latitude, longitude) -- the station of a
+ *      fan -- staged in the shared memory of every CTA by the bulk copy engine
+ *      (cp.async.bulk + mbarrier); samples outside of it gather as in mode 0.
+ * Results are byte-identical in all modes (tests/test_gpu_trace.py); the device-pointer
+ * trace calls honour the mode, the streamed / compact ones gather as in mode 0. See
+ * DESIGN.md section 3 for what each mode measures. latitude / longitude: mode 2 only. */
+TURTLE_API enum turtle_return turtle_plan_gather_set(struct turtle_plan * plan, int mode,
+    double latitude, double longitude);
 
 /* ---- whole rays: reset, query, then step until the rule stops the ray ------ */
 TURTLE_API enum turtle_return turtle_stepper_trace_batch(
@@ -329,6 +344,13 @@ TURTLE_API enum turtle_return turtle_map_elevation_batch(
 TURTLE_API enum turtle_return turtle_map_elevation_batch_device(
     struct turtle_map * map, size_t n, const double * x, const double * y,
     double * z, int * inside, void * stream);
+/* Node gathers of the batched elevation queries of `map` (the map-side twin of
+ * turtle_plan_gather_set). 0 (default): four 16-bit loads from the row-major mirror -- two
+ * 32-byte sectors per query. 1: ONE 8-byte load from a cell-packed second copy of the grid
+ * (cell (ix, iy) = its four nodes; 4 x the bytes of the mirror, built on the device at the
+ * next query) -- one sector per query, which is what a random-access query stream pays
+ * for. Same bits either way. */
+TURTLE_API void turtle_map_gather_set(struct turtle_map * map, int mode);
 /* Fused ECEF -> geodetic -> (projection) -> bilinear elevation: one pass over the
  * points, no intermediate arrays in HBM. latitude/longitude/altitude may be NULL. */
 TURTLE_API enum turtle_return turtle_map_elevation_ecef_batch(
@@ -363,6 +385,26 @@ TURTLE_API enum turtle_return turtle_map_gradient_batch(
 TURTLE_API enum turtle_return turtle_map_gradient_batch_device(
     struct turtle_map * map, size_t n, const double * x, const double * y,
     double * gx, double * gy, int * inside, void * stream);
+
+/* ---- stack queries (ref: turtle_stack_elevation, src/turtle/stack.c:338-361, and
+ * turtle_stack_gradient, stack.c:364-388) on the resident tiles of a plan.
+ * `stack` counts the stacks of the stepper in the order they were first added
+ * (turtle_stepper_add_stack). The tile that answers an elevation query answers the gradient
+ * query, with the bits of the scalar calls (turtle_map_gradient's first-row behaviour,
+ * map.c:353, included). Outside of every tile: inside[i] = 0 and the outputs are 0
+ * (stack.c:349-355,376-380); with inside == NULL that is not reported at all. */
+TURTLE_API enum turtle_return turtle_stack_elevation_batch(struct turtle_plan * plan, int stack,
+    size_t n, const double * latitude, const double * longitude, double * elevation,
+    int * inside);
+TURTLE_API enum turtle_return turtle_stack_elevation_batch_device(struct turtle_plan * plan,
+    int stack, size_t n, const double * latitude, const double * longitude, double * elevation,
+    int * inside, void * stream);
+TURTLE_API enum turtle_return turtle_stack_gradient_batch(struct turtle_plan * plan, int stack,
+    size_t n, const double * latitude, const double * longitude, double * glat, double * glon,
+    int * inside);
+TURTLE_API enum turtle_return turtle_stack_gradient_batch_device(struct turtle_plan * plan,
+    int stack, size_t n, const double * latitude, const double * longitude, double * glat,
+    double * glon, int * inside, void * stream);
 
 /* ---- host bulk set-up ---------------------------------------------------------*/
 /* turtle_map_fill for every node: elevation[iy * nx + ix] (ref: map.c:183-203).

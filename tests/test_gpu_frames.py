@@ -137,6 +137,34 @@ def test_map_gradient_bit_exact(ora):
     assert (np.abs(gx[gin == 1]) > 0).mean() > 0.9
 
 
+def test_stack_elevation_and_gradient_bit_exact(small_stack):
+    """turtle_stack_elevation_batch / turtle_stack_gradient_batch on the resident tiles of a
+    plan vs the reference's scalar calls (stack.c:338-388): + - * / only, bit-exact, over
+    tile interiors, shared tile edges, the missing tile and the outside of the stack."""
+    ref = H.Driver(H.best_oracle())
+    st = ref.stack_create(small_stack)
+    stepper = tb.Stepper(range=0.)
+    stepper.add_stack(tb.Stack(small_stack), 0.)
+    plan = stepper.freeze(0)
+    rng = np.random.default_rng(23)
+    n = 1 << 17
+    la = rng.uniform(44.9, 47.1, n)
+    lo = rng.uniform(1.9, 4.1, n)
+    k = 6000  # on and next to the tile edges (integer degrees) and the first rows of cells
+    la[:k] = np.round(la[:k]) + rng.choice([0., 1e-13, -1e-13, 1. / 1200 * 0.3], k)
+    lo[k:2 * k] = np.round(lo[k:2 * k]) + rng.choice([0., 1e-13, -1e-13, 1. / 1200 * 0.3], k)
+    wz, win = ref.stack_elevation(st, la, lo)
+    gz, gin = plan.stack_elevation(0, la, lo)
+    assert np.array_equal(win, gin) and np.array_equal(wz, gz)
+    wla, wlo, win = ref.stack_gradient(st, la, lo)
+    gla, glo, gin = plan.stack_gradient(0, la, lo)
+    assert np.array_equal(win, gin)
+    assert np.array_equal(wla, gla) and np.array_equal(wlo, glo)
+    assert 0.5 < gin.mean() < 0.9  # the missing tile and the margin are outside
+    with pytest.raises(tb.TurtleError):
+        plan.stack_gradient(1, la[:4], lo[:4])
+
+
 def test_geoid_style_geodetic_map(ora):
     g = geoid_map()
     m = ora.map_create(g["nx"], g["ny"], g["x"], g["y"], g["z"], None, g["values"])

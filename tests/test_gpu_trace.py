@@ -178,6 +178,19 @@ def test_determinism_and_chunking(small_stack):
     plan.trace_device(n, torch.from_numpy(pos).cuda(), torch.from_numpy(dirs).cuda(), rule, d_res)
     torch.cuda.synchronize()
     assert d_res.cpu().numpy().tobytes() == a.tobytes()
+    # the node gathers of the single-stack kernel: cell-packed tiles (one 8-byte load per
+    # sample), a shared-memory window staged by the bulk copy engine -- same answers
+    d_pos, d_dir = torch.from_numpy(pos).cuda(), torch.from_numpy(dirs).cuda()
+    for mode in (1, 2):
+        plan.gather_set(mode, 45.4, 2.6)
+        d_res.zero_()
+        plan.trace_device(n, d_pos, d_dir, rule, d_res)
+        torch.cuda.synchronize()
+        assert d_res.cpu().numpy().tobytes() == a.tobytes(), mode
+        if mode == 2:  # the station sits in the window: a good part of the samples hit it
+            c = plan.counters(sync=True)
+            assert 0 < c["window_hits"] <= c["samples"]
+    plan.gather_set(0)
     # a permutation of the rays permutes the results (no cross-ray state)
     perm = np.random.default_rng(3).permutation(n)
     p = plan.trace(pos[perm], dirs[perm], rule)

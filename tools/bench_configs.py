@@ -33,13 +33,35 @@ from oracle import parity as P  # noqa: E402
 from tests.common import Scene  # noqa: E402
 from turtle_b200 import synth  # noqa: E402
 
-DEV = "cuda:0"
+RANK = int(os.environ.get("RANK", "0"))
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+LOCAL = int(os.environ.get("LOCAL_RANK", "0"))
+DEV = "cuda:%d" % LOCAL
+
+
+def job_max(ms):
+    """Whole-job time of a sharded measurement: the slowest rank (device time, max over ranks)."""
+    if WORLD == 1:
+        return ms, [ms]
+    import torch.distributed as dist
+    t = torch.tensor([ms], device=DEV, dtype=torch.float64)
+    every = [torch.zeros_like(t) for _ in range(WORLD)]
+    dist.all_gather(every, t)
+    return max(float(x.item()) for x in every), [round(float(x.item()), 3) for x in every]
+
+
+def emit(line):
+    """ONE JSON line per job, from rank 0."""
+    if RANK == 0:
+        print(json.dumps(line), flush=True)
 
 
 def timed(fn, steps, warmup=3):
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
+    if WORLD > 1:
+        torch.distributed.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -51,8 +73,11 @@ def timed(fn, steps, warmup=3):
 
 def trace_config(name, scene, pos, dirs, rule_o, rule_g, args, ops_per_sample, note):
     stepper, maps, stacks = scene.product()
-    plan = stepper.freeze(0)
+    plan = stepper.freeze(LOCAL)
     plan.schedule_set(args.schedule)
+    n_job = len(pos)
+    if WORLD > 1:  # rays sharded with a stride (spreads the heavy tail), DEM replicated
+        pos, dirs = np.ascontiguousarray(pos[RANK::WORLD]), np.ascontiguousarray(dirs[RANK::WORLD])
     n = len(pos)
     d_pos, d_dir = torch.from_numpy(pos).to(DEV), torch.from_numpy(dirs).to(DEV)
     d_res = torch.empty((n, 96), dtype=torch.uint8, device=DEV)
@@ -61,12 +86,38 @@ def trace_config(name, scene, pos, dirs, rule_o, rule_g, args, ops_per_sample, n
                                max_steps=args.max_steps)
         rule_o = H.rule(rule_o.altitude_max, length_max=rule_o.length_max,
                         max_steps=args.max_steps)
-    ms = timed(lambda: plan.trace_device(n, d_pos, d_dir, rule_g, d_res), args.steps, args.warmup)
+    ms_rank = timed(lambda: plan.trace_device(n, d_pos, d_dir, rule_g, d_res), args.steps, args.warmup)
+    ms, per_rank = job_max(ms_rank)
     c = plan.counters(sync=True)
+    piped = None
+    if args.inflight > 1:
+        # Steady state with several batches in flight on one plan: a launch ends when its
+        # slowest ray does, and the SMs its persistent CTAs have left are taken by the next
+        # batch (the CPU hides long rays behind each other the same way,
+        # examples/example-pthread.c:66-114). One stream and one result array per batch in
+        # flight; the device-pointer calls are asynchronous.
+        k = args.inflight
+        streams = [torch.cuda.Stream() for _ in range(k)]
+        outs = [torch.empty((n, 96), dtype=torch.uint8, device=DEV) for _ in range(k)]
+        batches = max(2 * k, args.steps * k)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for b in range(batches):
+            st = streams[b % k]
+            plan.trace_device(n, d_pos, d_dir, rule_g, outs[b % k], stream=st.cuda_stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        same = all(bool((o == d_res).all()) for o in outs)
+        piped = {"batches_in_flight": k, "batches": batches, "ms_per_batch": 1e3 * wall / batches,
+                 "Mrays_per_s": n * batches / wall / 1e6, "results_identical": same,
+                 "single_launch_ms": ms}
     if args.no_cpu:
-        print(json.dumps({"config": name, "rays": n, "ms_per_step": ms, "Mrays_per_s": n / ms / 1e3,
-                          "samples": c["samples"], "steps": c["steps"], "rebuilds": c["rebuilds"],
-                          "Gsamples_per_s": c["samples"] / ms / 1e6}), flush=True)
+        emit({"config": name, "n_gpus": WORLD, "rays": n_job, "ms_per_step": ms,
+              "Mrays_per_s": n_job / ms / 1e3, "per_rank_ms": per_rank,
+              "samples": c["samples"], "steps": c["steps"], "rebuilds": c["rebuilds"],
+              "Gsamples_per_s": c["samples"] / ms_rank / 1e6, "pipelined": piped})
+        return
+    if RANK != 0:
         return
     got = d_res.cpu().numpy().view(tb.TRACE_RESULT).reshape(n)
     # reference on all cores, strided sample
@@ -82,19 +133,29 @@ def trace_config(name, scene, pos, dirs, rule_o, rule_g, args, ops_per_sample, n
         floor = P.report(want, fma)
     sys.stderr.write(P.table(rep, floor) + "\n")
     dfma = tb.dfma_peak(3)
-    achieved = ops_per_sample * c["samples"] / (ms * 1e-3) / 1e12
+    # executed FP64-pipe lane slots per sample: the committed ncu capture of this kernel on
+    # this configuration (tools/kernel_profiles.py), refused when the kernel has changed
+    lla = "_lla" if scene.range > 0 else ""
+    prof, prof_src = B.kernel_profile("%s_trace%s_proj" % (name, lla))
+    ops_per_sample = prof["fp64_lane_slots_per_sample"] if prof else None
+    achieved = ops_per_sample * c["samples"] / (ms_rank * 1e-3) / 1e12 if prof else None
     line = {
-        "config": name, "workload": note, "rays": n, "schedule": args.schedule, "ms_per_step": ms,
-        "Mrays_per_s": n / ms / 1e3, "ns_per_step": ms * 1e6 / max(c["steps"], 1),
+        "config": name, "workload": note, "n_gpus": WORLD, "rays": n_job, "rays_per_gpu": n,
+        "schedule": args.schedule, "ms_per_step": ms, "per_rank_ms": per_rank,
+        "Mrays_per_s": n_job / ms / 1e3, "ns_per_step": ms_rank * 1e6 / max(c["steps"], 1),
         "steps_per_ray": c["steps"] / n, "samples_per_step": c["samples"] / max(c["steps"], 1),
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": dfma / 1e3,
-                     "unit": "Tinst/s (FP64 pipe; FMA = 1)", "frac": achieved / (dfma / 1e3),
-                     "ops_per_sample": ops_per_sample},
+                     "unit": "Tinst/s (FP64 pipe; FMA = 1)",
+                     "frac": achieved / (dfma / 1e3) if prof else None,
+                     "ops_per_sample": ops_per_sample, "ops_source": prof_src,
+                     "active_threads_per_inst": prof["active_threads_per_inst"] if prof else None,
+                     "issue_ceiling": prof["issue_ceiling"] if prof else None,
+                     "dram_bytes_per_sample": prof["dram_bytes_per_sample"] if prof else None},
         "cpu_baseline": {"Mrays_per_s": len(want) / seconds / 1e6, "cores": os.cpu_count(),
                          "ns_per_step": 1e9 * seconds / max(steps, 1), "kind": "reference"
                          if H.best_oracle() == H.REF else "port",
                          "sample": "every %d-th ray (%d rays)" % (stride, len(want))},
-        "rebuilds_per_sample": c.get("rebuilds", 0) / max(c["samples"], 1),
+        "rebuilds_per_sample": c.get("rebuilds", 0) / max(c["samples"], 1), "pipelined": piped,
         "parity": rep, "noise_floor": floor,
         "parity_vs_floor": P.against_floor(rep, floor) if floor else None,
         "status_counts": np.bincount(got["status"], minlength=5).tolist(),
@@ -104,23 +165,28 @@ def trace_config(name, scene, pos, dirs, rule_o, rule_g, args, ops_per_sample, n
     print(json.dumps(line), flush=True)
 
 
-def c1(args):
+def c1_inputs(n, rg):
+    """Scene and rays of configuration 1: 2001 x 2001 UTM map over a flat
+    bottom, n-ray fan from the map centre + 1 m."""
     n_map = 2001
     x = (486000., 506000.)
     y = (5057000., 5077000.)
     vals = synth.fbm_grid(np.arange(n_map) / 3., np.arange(n_map) / 3.) * 3000.
     mp = dict(nx=n_map, ny=n_map, x=x, y=y, z=(0., 3000.), projection="UTM 31N", values=vals)
     scene = Scene(maps=[mp], ops=[(H.ADD_FLAT, 0, -100.), (H.ADD_LAYER, 0, 0.),
-                                  (H.ADD_MAP, 0, 0.)], range=args.range)
+                                  (H.ADD_MAP, 0, 0.)], range=rg)
     ora = scene.oracle()
     lat, lon = ora.project("UTM 31N", [0.5 * (x[0] + x[1])], [0.5 * (y[0] + y[1])], inverse=True)
     origin, idx = ora.position(lat, lon, [1.0], 1)
-    n = args.rays or (1 << 20)
     az, el = synth.golden_fan(n)
     dirs = synth.np_from_horizontal(np.full(n, lat[0]), np.full(n, lon[0]), az, el)
-    pos = np.repeat(origin, n, 0)
-    # UTM map sample = geodetic transform (~340) + UTM projection (~810) + bilinear
-    trace_config("c1", scene, pos, dirs, H.rule(3100.), tb.trace_rule(3100.), args, 1190.,
+    return scene, np.repeat(origin, n, 0), dirs
+
+
+def c1(args):
+    n = args.rays or (1 << 20)
+    scene, pos, dirs = c1_inputs(n, args.range)
+    trace_config("c1", scene, pos, dirs, H.rule(3100.), tb.trace_rule(3100.), args, None,
                  "1 Mi-ray fan from the centre of a 2001x2001 UTM 31N map (10 m pitch) over a "
                  "flat bottom at -100 m, range %g, stop alt > 3100 m | 1e5 steps" % args.range)
 
@@ -142,18 +208,21 @@ def layered_scene(rg):
                  ops=[(H.ADD_FLAT, 0, 0.), (H.ADD_STACK, 0, 0.), (H.ADD_MAP, 0, 0.)], range=rg)
 
 
-def c3(args):
-    scene = layered_scene(10. if args.range is None else args.range)
-    n = args.rays or (1 << 26)  # BASELINE.json configs[2]: 64 Mi rays
+def c3_inputs(n, rg):
+    """Scene and rays of configuration 3: flat / 3 x 3 stack / Lambert map in one layer,
+    n random rays (origins in the stack box + 0.1 deg, isotropic directions)."""
+    scene = layered_scene(rg)
     lat = B.STACK_LAT0 - 0.1 + (B.STACK_N + 0.2) * synth.random_uniform(n, 0xC3, 0)
     lon = B.STACK_LON0 - 0.1 + (B.STACK_N + 0.2) * synth.random_uniform(n, 0xC3, 1)
     alt = -500. + 5500. * synth.random_uniform(n, 0xC3, 2)
-    pos = synth.np_ecef_from_geodetic(lat, lon, alt)
-    dirs = synth.random_unit(n, 0xC3)
-    # per sample: geodetic transform + stack lookup; the Lambert map is only evaluated
-    # inside its 10 km footprint -> ~385 FP64 instructions on average
+    return scene, synth.np_ecef_from_geodetic(lat, lon, alt), synth.random_unit(n, 0xC3)
+
+
+def c3(args):
+    n = args.rays or (1 << 26)  # BASELINE.json configs[2]: 64 Mi rays
+    scene, pos, dirs = c3_inputs(n, 10. if args.range is None else args.range)
     trace_config("c3", scene, pos, dirs, H.rule(9000., length_max=1e5),
-                 tb.trace_rule(9000., length_max=1e5), args, 385.,
+                 tb.trace_rule(9000., length_max=1e5), args, None,
                  "random rays (origins in the stack bbox + 0.1 deg, alt -500..5000 m, isotropic) "
                  "through flat(0) / 3x3 SRTMGL1 stack / 2001x2001 Lambert-93 map (5 m), range "
                  "%g, stop leaves data | alt > 9000 m | path > 100 km | 1e5 steps" % scene.range)
@@ -162,17 +231,18 @@ def c3(args):
 def c4(args):
     scene = layered_scene(1. if args.range is None else args.range)
     stepper, maps, stacks = scene.product()
-    plan = stepper.freeze(0)
-    n = args.rays or (1 << 23)
+    plan = stepper.freeze(LOCAL)
+    n_job = args.rays or (1 << 23)
     k = args.walk
-    lat = 45.5 + 2. * synth.random_uniform(n, 0xC4, 0)
-    lon = 2.5 + 2. * synth.random_uniform(n, 0xC4, 1)
-    h = -50. + 100. * synth.random_uniform(n, 0xC4, 2)
+    lat = (45.5 + 2. * synth.random_uniform(n_job, 0xC4, 0))[RANK::WORLD]
+    lon = (2.5 + 2. * synth.random_uniform(n_job, 0xC4, 1))[RANK::WORLD]
+    h = (-50. + 100. * synth.random_uniform(n_job, 0xC4, 2))[RANK::WORLD]
+    n = len(lat)  # particles of this rank (strided shard)
     origin, idx = plan.position(lat, lon, h, 0)
     assert (idx >= 0).all()
     d_pos0 = torch.from_numpy(origin).to(DEV)
     gen = torch.Generator(device=DEV)
-    gen.manual_seed(0xC4)
+    gen.manual_seed(0xC4 + RANK)
 
     def directions():
         u = torch.rand((n, 2), generator=gen, device=DEV, dtype=torch.float64)
@@ -191,8 +261,10 @@ def c4(args):
     for rep in range(2):  # pass 0 = warm-up, pass 1 = timed
         states.reset()
         d_pos = d_pos0.clone()
-        gen.manual_seed(0xC4)
+        gen.manual_seed(0xC4 + RANK)
         total_ms = 0.
+        if WORLD > 1:
+            torch.distributed.barrier()
         sample_dirs, got_step, got_alt, got_idx = [], [], [], []
         for j in range(k):
             d_dir = directions()
@@ -209,10 +281,14 @@ def c4(args):
                 got_step.append(d_step[::stride].cpu().numpy())
                 got_alt.append(d_alt[::stride].cpu().numpy())
                 got_idx.append(d_idx[::stride].cpu().numpy())
+    ms_rank = total_ms
+    total_ms, per_rank = job_max(ms_rank)
     if args.no_cpu:
-        print(json.dumps({"config": "c4", "particles": n, "walk_steps": k, "ms_total": total_ms,
-                          "Msteps_per_s": n * k / total_ms / 1e3,
-                          "rebuilds_per_step": rebuilds / (n * k)}), flush=True)
+        emit({"config": "c4", "n_gpus": WORLD, "particles": n_job, "walk_steps": k,
+              "ms_total": total_ms, "per_rank_ms": per_rank,
+              "Msteps_per_s": n_job * k / total_ms / 1e3, "rebuilds_per_step": rebuilds / (n * k)})
+        return
+    if RANK != 0:
         return
     ora = scene.oracle(locked=True)
     want = ora.walk(origin[::stride], np.stack(sample_dirs), threads=os.cpu_count())
@@ -223,9 +299,10 @@ def c4(args):
     line = {
         "config": "c4", "workload": "%d particles x %d turtle_stepper_step, fresh isotropic "
         "direction each step, start within +-50 m of the ground; geometry of c3, range %g, "
-        "per-particle stepper state on the device" % (n, k, scene.range),
-        "particles": n, "walk_steps": k, "ms_total": total_ms,
-        "Msteps_per_s": n * k / total_ms / 1e3, "ns_per_step": total_ms * 1e6 / (n * k),
+        "per-particle stepper state on the device" % (n_job, k, scene.range),
+        "n_gpus": WORLD, "particles": n_job, "walk_steps": k, "ms_total": total_ms,
+        "per_rank_ms": per_rank,
+        "Msteps_per_s": n_job * k / total_ms / 1e3, "ns_per_step": total_ms * 1e6 / (n_job * k),
         "state_bytes_per_particle": int(states.bytes_per_particle),
         "rebuilds_per_step": rebuilds / (n * k),
         "cpu_baseline": {"Msteps_per_s": m * k / want["seconds"] / 1e6, "cores": os.cpu_count(),
@@ -240,28 +317,39 @@ def c4(args):
     print(json.dumps(line), flush=True)
 
 
-def c5(args):
-    n_map = args.map_nodes
+def c5_map(n_map):
+    """The geodetic map of configuration 5: n_map x n_map nodes over a 5.5 x 5.5 degree box,
+    a cheap SEPARABLE synthetic terrain (node (ix, iy) = rint(row[ix] + col[iy]), z0 = 0,
+    dz = 1) so that the host fill stays tractable and every node is known in closed form.
+    -> (map, row, col, (lon0, lat0, box))"""
+    import ctypes as C
+    from turtle_b200._lib import lib
     box = 5.5
     lat0, lon0 = 44., 1.
-    # 20k x 20k nodes: a cheap separable synthetic terrain keeps the host fill tractable
     gx = np.arange(n_map, dtype=np.float64)
     row = 2500. + 1000. * np.sin(gx * 0.013) + 300. * np.sin(gx * 0.171)
     col = 400. * np.cos(gx * 0.007) + 100. * np.sin(gx * 0.31)
-    t0 = time.time()
     mp = tb.Map(n_map, n_map, (lon0, lon0 + box), (lat0, lat0 + box), (0., 65535.), None)
     chunk = 1000
-    import ctypes as C
-    from turtle_b200._lib import lib
     for j0 in range(0, n_map, chunk):
         j1 = min(n_map, j0 + chunk)
         block = np.ascontiguousarray(np.rint(row[None, :] + col[j0:j1, None]))
         tb.api._check(lib.turtle_map_fill_rows(mp.handle, j0, j1 - j0,
                                                block.ctypes.data_as(C.c_void_p)))
+    return mp, row, col, (lon0, lat0, box)
+
+
+def c5(args):
+    import ctypes as C
+    from turtle_b200._lib import lib
+    n_map = args.map_nodes
+    t0 = time.time()
+    mp, row, col, (lon0, lat0, box) = c5_map(n_map)
     fill_s = time.time() - t0
-    n = args.rays or (1 << 30)
+    n_job = args.rays or (1 << 30)
+    n = n_job // WORLD  # a contiguous chunk of the points per rank
     gen = torch.Generator(device=DEV)
-    gen.manual_seed(0xC5)
+    gen.manual_seed(0xC5 + RANK)
     d_ecef = torch.empty((n, 3), dtype=torch.float64, device=DEV)
     piece = 1 << 26
     for i0 in range(0, n, piece):
@@ -287,9 +375,14 @@ def c5(args):
     ms_fused = timed(lambda: tb.api._check(lib.turtle_map_elevation_ecef_batch_device(
         mp.handle, n, P(d_ecef), P(d_lat), P(d_lon), P(d_alt), P(d_z), P(d_in), None)), args.steps,
         args.warmup)
+    (ms_geo, _), (ms_map, _), (ms_fused, per_rank) = job_max(ms_geo), job_max(ms_map), job_max(ms_fused)
     if args.no_cpu:
-        print(json.dumps({"config": "c5", "points": n, "ms_to_geodetic": ms_geo,
-                          "ms_map_elevation": ms_map, "ms_fused": ms_fused}), flush=True)
+        emit({"config": "c5", "n_gpus": WORLD, "points": n_job, "ms_to_geodetic": ms_geo,
+              "ms_map_elevation": ms_map, "ms_fused": ms_fused, "per_rank_ms_fused": per_rank,
+              "Gpoints_per_s": {"to_geodetic": n_job / ms_geo / 1e6, "map_elevation": n_job / ms_map / 1e6,
+                                "fused": n_job / ms_fused / 1e6}})
+        return
+    if RANK != 0:
         return
     # oracle on a strided sample
     stride = max(1, n // args.cpu_rays)
@@ -315,17 +408,34 @@ def c5(args):
         if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.
     dfma = tb.dfma_peak(3)
 
-    def roof(ms, nbytes, ops):
-        return {"GB_per_s": n * nbytes / ms / 1e6, "hbm_frac": n * nbytes / ms / 1e6 / hbm,
-                "fp64_Tinst_per_s": n * ops / ms / 1e9, "fp64_frac": n * ops / ms / 1e9 / (dfma / 1e3)}
+    def roof(ms, nbytes, profile_name):
+        """Both roofs of a query kernel: algorithmic bytes per point against the measured HBM
+        bandwidth, executed FP64-pipe lane slots per point (committed ncu capture, refused
+        when stale) against the measured DFMA peak; plus the DRAM bytes actually moved."""
+        out = {"GB_per_s": n * nbytes / ms / 1e6, "hbm_frac": n * nbytes / ms / 1e6 / hbm,
+               "algorithmic_bytes_per_point": nbytes}
+        prof, src = B.kernel_profile(profile_name)
+        out["profile"] = src
+        if prof is not None:
+            ops = prof["fp64_lane_slots_per_sample"]
+            out.update({"fp64_lane_slots_per_point": ops,
+                        "fp64_Tinst_per_s": n * ops / ms / 1e9,
+                        "fp64_frac": n * ops / ms / 1e9 / (dfma / 1e3),
+                        "dram_bytes_per_point": prof["dram_bytes_per_sample"],
+                        "bound": "fp64" if n * ops / ms / 1e9 / (dfma / 1e3) >
+                        n * nbytes / ms / 1e6 / hbm else "hbm"})
+        return out
     line = {
         "config": "c5", "workload": "%d ECEF points (uniform over the map box + 0.05 deg, alt "
         "0-5000 m) -> turtle_ecef_to_geodetic_batch, turtle_map_elevation_batch and the fused "
-        "kernel on a %dx%d uint16 geodetic map (%.0f MB)" % (n, n_map, n_map, n_map * n_map * 2 / 1e6),
-        "points": n, "map_fill_seconds": fill_s,
-        "to_geodetic": dict(ms=ms_geo, Gpoints_per_s=n / ms_geo / 1e6, **roof(ms_geo, 48, 340)),
-        "map_elevation": dict(ms=ms_map, Gpoints_per_s=n / ms_map / 1e6, **roof(ms_map, 36, 70)),
-        "fused": dict(ms=ms_fused, Gpoints_per_s=n / ms_fused / 1e6, **roof(ms_fused, 68, 410)),
+        "kernel on a %dx%d uint16 geodetic map (%.0f MB)" % (n_job, n_map, n_map, n_map * n_map * 2 / 1e6),
+        "n_gpus": WORLD, "points": n_job, "points_per_gpu": n, "map_fill_seconds": fill_s,
+        "to_geodetic": dict(ms=ms_geo, Gpoints_per_s=n_job / ms_geo / 1e6,
+                            **roof(ms_geo, 48, "c5_to_geodetic")),
+        "map_elevation": dict(ms=ms_map, Gpoints_per_s=n_job / ms_map / 1e6,
+                              **roof(ms_map, 36, "c5_map_elevation")),
+        "fused": dict(ms=ms_fused, Gpoints_per_s=n_job / ms_fused / 1e6,
+                      **roof(ms_fused, 68, "c5_map_elevation_ecef")),
         "peaks": {"hbm_GB_per_s": hbm, "fp64_Tinst_per_s": dfma / 1e3},
         "cpu_baseline": {"to_geodetic_Mpoints_per_s_1core": len(wla) / t_geo / 1e6,
                          "sample": "every %d-th point (%d points), 1 thread" % (stride, len(wla))},
@@ -350,13 +460,25 @@ def main():
     ap.add_argument("--map-nodes", type=int, default=20000)
     ap.add_argument("--schedule", type=int, default=0)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--inflight", type=int, default=0,
+                    help="also measure the steady state with this many batches in flight")
     ap.add_argument("--max-steps", type=int, default=0,
                     help="profiling: stop rays after this many steps (bounds the launch tail)")
     ap.add_argument("--no-cpu", action="store_true", help="GPU part only (ncu captures)")
     args = ap.parse_args()
     if args.config == "c1" and args.range is None:
         args.range = 0.
+    torch.cuda.set_device(LOCAL)
+    if WORLD > 1:  # one process per GPU (torchrun): --rays is the size of the WHOLE job
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/turtle_b200_nccl.%h.%p.log")
+        torch.distributed.init_process_group("nccl", device_id=torch.device(DEV))
+        if RANK == 0:
+            B.make_stack()
+        torch.distributed.barrier()
     {"c1": c1, "c3": c3, "c4": c4, "c5": c5}[args.config](args)
+    if WORLD > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -1,8 +1,9 @@
 """Turn `ncu --set full` captures (.ncu-rep, read here: no GPU needed) into the numbers the
 rooflines use, so that no measurement tool carries a hand-typed constant.
 
-    python tools/kernel_profiles.py ROLE=REP:UNITS:RAYS[:LOG] ... [--out profiles/r02_kernels.json]
+    python tools/kernel_profiles.py NAME=ROLE@REP:UNITS:RAYS ... [--out profiles/r02_kernels.json]
 
+NAME   the key of the entry: configuration + kernel ("c2_trace_stack", "c4_walk_lla_proj", ...)
 ROLE   the role name of turtle_b200_kernel_info ("trace_stack", "walk_lla_proj", ...)
 REP    the capture of ONE launch of that kernel
 UNITS  geometry samples (trace / walk kernels) or points (query kernels) of that launch,
@@ -108,11 +109,14 @@ def main():
         del args[i:i + 2]
     table = json.load(open(out_path)) if os.path.exists(out_path) else {}
     for a in args:
-        role, rest = a.split("=", 1)
+        name, rest = a.split("=", 1)
+        role, rest = rest.split("@", 1)
         parts = rest.split(":")
         rep, units, rays = parts[0], int(float(parts[1])), int(float(parts[2]))
         entry = profile(rep, units, rays)
-        entry["source"] = "r02_%s.md" % role
+        entry["role"] = role
+        entry["source"] = "r02_%s.md" % name
+        role = name
         entry["capture"] = os.path.basename(rep)
         table[role] = entry
         md = os.path.join(ROOT, "profiles", entry["source"])

@@ -63,7 +63,8 @@ class PlanCounters(C.Structure):
     """struct turtle_plan_counters (include/turtle_b200.h)."""
     _fields_ = [("rays", C.c_uint64), ("steps", C.c_uint64),
                 ("samples", C.c_uint64), ("launches", C.c_uint64),
-                ("kernel_ms", C.c_double), ("rebuilds", C.c_uint64)]
+                ("kernel_ms", C.c_double), ("rebuilds", C.c_uint64),
+                ("window_hits", C.c_uint64)]
 
 
 ERROR_HANDLER = C.CFUNCTYPE(None, C.c_int, C.c_void_p, C.c_char_p)
@@ -144,6 +145,7 @@ SIGNATURES = {
     "turtle_plan_schedule_set": (None, [_P, _I]),
     "turtle_plan_specialise_set": (None, [_P, _I]),
     "turtle_plan_pipeline_set": (None, [_P, _I]),
+    "turtle_plan_gather_set": (_I, [_P, _I, _D, _D]),
     "turtle_stack_tiles_loaded": (_I, [_P]),
     "turtle_map_resample": (_I, [_P, _P, _I, C.POINTER(C.c_size_t)]),
     "turtle_stepper_freeze_region": (_I, [_P, _I, C.POINTER(Residency), _PP]),
@@ -186,6 +188,7 @@ SIGNATURES = {
     "turtle_ecef_from_horizontal_batch": (_I, [_N, _P, _P, _P, _P, _P]),
     "turtle_ecef_from_horizontal_batch_device": (_I, [_N, _P, _P, _P, _P, _P, _P]),
     # elevation
+    "turtle_map_gather_set": (None, [_P, _I]),
     "turtle_map_elevation_batch": (_I, [_P, _N, _P, _P, _P, _P]),
     "turtle_map_elevation_batch_device": (_I, [_P, _N, _P, _P, _P, _P, _P]),
     "turtle_map_elevation_ecef_batch": (_I, [_P, _N, _P, _P, _P, _P, _P, _P]),
@@ -196,6 +199,10 @@ SIGNATURES = {
     "turtle_projection_unproject_batch_device": (_I, [_P, _N, _P, _P, _P, _P, _P]),
     "turtle_map_gradient_batch": (_I, [_P, _N, _P, _P, _P, _P, _P]),
     "turtle_map_gradient_batch_device": (_I, [_P, _N, _P, _P, _P, _P, _P, _P]),
+    "turtle_stack_elevation_batch": (_I, [_P, _I, _N, _P, _P, _P, _P]),
+    "turtle_stack_elevation_batch_device": (_I, [_P, _I, _N, _P, _P, _P, _P, _P]),
+    "turtle_stack_gradient_batch": (_I, [_P, _I, _N, _P, _P, _P, _P, _P]),
+    "turtle_stack_gradient_batch_device": (_I, [_P, _I, _N, _P, _P, _P, _P, _P, _P]),
     "turtle_map_fill_batch": (_I, [_P, _P]),
     "turtle_map_fill_rows": (_I, [_P, _I, _I, _P]),
     # utilities

@@ -415,7 +415,11 @@ class Plan:
         c = PlanCounters()
         lib.turtle_plan_counters_get(self._p, C.byref(c))
         return dict(rays=c.rays, steps=c.steps, samples=c.samples, launches=c.launches,
-                    kernel_ms=c.kernel_ms, rebuilds=c.rebuilds)
+                    kernel_ms=c.kernel_ms, rebuilds=c.rebuilds, window_hits=c.window_hits)
+
+    def gather_set(self, mode, latitude=0., longitude=0.):
+        """turtle_plan_gather_set: 0 global 16-bit loads, 1 cell-packed copy, 2 window."""
+        _check(lib.turtle_plan_gather_set(self._p, mode, latitude, longitude))
 
     def trace(self, position, direction, rule, results=None):
         """Host arrays in, host records out (turtle_stepper_trace_batch)."""
@@ -534,6 +538,23 @@ class Plan:
         _check(lib.turtle_stepper_position_batch(self._p, len(la), _ptr(la), _ptr(lo), _ptr(h),
                                                  layer, _ptr(pos), _ptr(idx)))
         return pos, idx
+
+    def stack_elevation(self, stack, latitude, longitude):
+        """turtle_stack_elevation_batch on stack `stack` of the plan -> (z, inside)."""
+        la, lo = _f8(latitude), _f8(longitude)
+        z, inside = np.zeros(len(la)), np.zeros(len(la), dtype=np.int32)
+        _check(lib.turtle_stack_elevation_batch(self._p, stack, len(la), _ptr(la), _ptr(lo),
+                                                _ptr(z), _ptr(inside)))
+        return z, inside
+
+    def stack_gradient(self, stack, latitude, longitude):
+        """turtle_stack_gradient_batch -> (glat, glon, inside)."""
+        la, lo = _f8(latitude), _f8(longitude)
+        glat, glon = np.zeros(len(la)), np.zeros(len(la))
+        inside = np.zeros(len(la), dtype=np.int32)
+        _check(lib.turtle_stack_gradient_batch(self._p, stack, len(la), _ptr(la), _ptr(lo),
+                                               _ptr(glat), _ptr(glon), _ptr(inside)))
+        return glat, glon, inside
 
     def states(self, n):
         return States(self, n)

@@ -22,6 +22,9 @@ struct tb_device_mirror {
         uint16_t * nodes = nullptr;
         int pitch = 0;
         uint64_t version = 0;
+        /* cell-packed second copy (tb::NodesPacked), built when the map asks for it */
+        void * packed = nullptr;
+        uint64_t packed_version = 0;
 };
 
 /* ref: struct turtle_projection, projection.h:37-47 */
@@ -44,6 +47,7 @@ struct turtle_map {
         std::vector<uint16_t> nodes;
         struct turtle_stack * stack;
         uint64_t version; /* bumped by turtle_map_fill */
+        int gather = 0;   /* turtle_map_gather_set: 0 row-major gathers, 1 cell-packed copy */
         std::vector<tb_device_mirror> mirrors;
 };
 

@@ -81,7 +81,13 @@ struct TraceArgs {
         /* medium changes of every ray (turtle_stepper_trace_crossings), or NULL */
         turtle_trace_crossing * crossings;
         int max_crossings;
-        /* fan input (turtle_stepper_trace_fan; position == NULL): every ray starts at
+};
+
+/* Compact input / output (turtle_stepper_trace_fan / _fields): a kernel parameter of its
+ * own, of the COMPACT kernels only -- the mere presence of these members in TraceArgs
+ * costs every trace kernel four registers. */
+struct CompactArgs {
+        /* fan input (turtle_stepper_trace_fan; TraceArgs::position == NULL): every ray starts at
          * fan_origin; direction of ray (i, j) from the host's sines / cosines of the
          * angles, fan_az[i] = { sin az, cos az }, fan_el[j] = { cos el, sin el }, and the
          * local East / North / Up vectors (ecef.c:136-178) */
@@ -92,6 +98,36 @@ struct TraceArgs {
         /* field outputs (turtle_trace_fields: device arrays, any NULL), when use_fields */
         turtle_trace_fields fields;
         int use_fields;
+};
+
+struct NoCompactArgs {
+        int unused;
+};
+
+/* How the trace kernel of a uniform stack gathers its nodes (turtle_plan_gather_set):
+ * GATHER_GLOBAL four 16-bit loads, GATHER_PACKED one 8-byte load from the cell-packed copy
+ * of the tiles, GATHER_WINDOW a window of one tile staged in shared memory. */
+enum { GATHER_GLOBAL = 0, GATHER_PACKED = 1, GATHER_WINDOW = 2 };
+enum { WINDOW_NODES = 64 }; /* nodes per side of the window: 8 kB of shared memory per CTA */
+
+/* The window of a GATHER_WINDOW kernel: WINDOW_NODES x WINDOW_NODES nodes of ONE tile,
+ * first node (x0, y0); x0 is a multiple of 8 nodes (16-byte aligned rows for the bulk
+ * copies). */
+struct WindowArgs {
+        const uint16_t * tile; /* row-major nodes of the tile, as in its TileRec */
+        int x0, y0, pitch;
+        unsigned long long * hits; /* [0] samples served by the window, [1] all samples */
+};
+
+/* Third kernel parameter by variant (never both: the compact kernels gather globally). */
+template <bool COMPACT, int GATHER = GATHER_GLOBAL> struct ExtraOf {
+        typedef NoCompactArgs type;
+};
+template <> struct ExtraOf<true, GATHER_GLOBAL> {
+        typedef CompactArgs type;
+};
+template <> struct ExtraOf<false, GATHER_WINDOW> {
+        typedef WindowArgs type;
 };
 
 #define STREAM_ABORT (~0ull)
@@ -107,7 +143,7 @@ __device__ __forceinline__ unsigned long long global_ns()
 /* Streamed calls: a record must be visible before it is counted for its chunk. The fence
  * that guarantees it stalls the whole warp, so counts are deferred: a lane remembers what
  * it owes (chunk in the high bits, number of rays in the low 8) and the warp settles its
- * debts with ONE fence -- every 128 iterations, when it runs dry, or when a lane would owe
+ * debts with ONE fence -- every 1024 iterations, when it runs dry, or when a lane would owe
  * to two chunks. The records are stored by other lanes of the warp than the one that owes
  * (warp-cooperative write-out below): every lane fences its own stores, the warp
  * synchronises, then the owners count. Warp uniform. */
@@ -167,11 +203,146 @@ typedef LaneStoreT<N_F, N_I> LaneStore;
 
 __device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
 
+/* Compact input / output of the trace kernel (COMPACT variants only: the kernels of
+ * turtle_stepper_trace_fan / _fields; the others do not carry this code). */
+
+/* Direction of ray r of a fan: the products and sums of turtle_ecef_from_horizontal
+ * (ecef.c:170-177) on the host's sines / cosines of the two angles. */
+__device__ __forceinline__ void fan_ray(const CompactArgs & A, unsigned long long r, double pos[3],
+    double dir[3])
+{
+        const unsigned long long per_band = A.fan_naz * A.fan_bundle;
+        const unsigned long long rr = r + A.fan_ray0;
+        const unsigned long long band = rr / per_band;
+        const unsigned long long rem = rr - band * per_band;
+        const unsigned long long i = rem / A.fan_bundle;
+        const unsigned long long j = band * A.fan_bundle + (rem - i * A.fan_bundle);
+        const double2 az = __ldg(A.fan_az + i);
+        const double2 el = __ldg(A.fan_el + j);
+        const double r0 = el.x * az.x, r1 = el.x * az.y, r2 = el.y;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+                pos[c] = A.fan_origin[c];
+                dir[c] = r0 * A.fan_e[c] + r1 * A.fan_n[c] + r2 * A.fan_u[c];
+        }
+}
+
+__device__ __forceinline__ void fan_ray(const NoCompactArgs &, unsigned long long, double *, double *) {}
+__device__ __forceinline__ void store_fields(const NoCompactArgs &, const double *, const int *) {}
+__device__ __forceinline__ bool wants_fields(const NoCompactArgs &) { return false; }
+__device__ __forceinline__ bool wants_fields(const WindowArgs &) { return false; }
+__device__ __forceinline__ void fan_ray(const WindowArgs &, unsigned long long, double *, double *) {}
+__device__ __forceinline__ void store_fields(const WindowArgs &, const double *, const int *) {}
+
+/* Nodes of a cell from the shared-memory window when the cell lies in it, else from
+ * global memory (tb::NodesGlobal). */
+struct NodesWindow {
+        const uint16_t * window;
+        const uint16_t * tile;
+        int x0, y0;
+        mutable unsigned hits;
+        __device__ __forceinline__ void fetch(const uint16_t * nodes, int pitch, int ix, int iy,
+            uint16_t r[4]) const
+        {
+                const unsigned dx = (unsigned)(ix - x0), dy = (unsigned)(iy - y0);
+                if ((nodes == tile) && (dx < WINDOW_NODES - 1u) && (dy < WINDOW_NODES - 1u)) {
+                        const uint16_t * w = window + dy * WINDOW_NODES + dx;
+                        r[0] = w[0];
+                        r[1] = w[1];
+                        r[2] = w[WINDOW_NODES];
+                        r[3] = w[WINDOW_NODES + 1];
+                        hits++;
+                } else {
+                        tb::NodesGlobal().fetch(nodes, pitch, ix, iy, r);
+                }
+        }
+};
+
+/* Stage the window: one bulk copy (cp.async.bulk, the TMA engine's 1-D form) per row,
+ * all completing on ONE mbarrier that every thread of the CTA then waits on. */
+__device__ __forceinline__ void window_load(uint16_t * window, unsigned long long * barrier,
+    const WindowArgs & W)
+{
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(barrier);
+        if (threadIdx.x == 0) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+                const unsigned row_bytes = WINDOW_NODES * (unsigned)sizeof(uint16_t);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                    "r"(row_bytes * WINDOW_NODES)
+                    : "memory");
+                for (int r = 0; r < WINDOW_NODES; r++) {
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(window + r * WINDOW_NODES);
+                        const uint16_t * src = W.tile + (size_t)(W.y0 + r) * (size_t)W.pitch + W.x0;
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+                            "[%0], [%1], %2, [%3];" ::"r"(dst),
+                            "l"(src), "r"(row_bytes), "r"(bar)
+                            : "memory");
+                }
+        }
+        unsigned done = 0u;
+        while (!done) {
+                asm volatile("{\n.reg .pred p;\n"
+                             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+                             "selp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(done)
+                             : "r"(bar)
+                             : "memory");
+        }
+}
+
+__device__ __forceinline__ void window_setup(NodesWindow & from, uint16_t * window,
+    unsigned long long * barrier, const WindowArgs & W)
+{
+        window_load(window, barrier, W);
+        from.tile = W.tile;
+        from.x0 = W.x0;
+        from.y0 = W.y0;
+}
+template <class Other>
+__device__ __forceinline__ void window_setup(NodesWindow &, uint16_t *, unsigned long long *,
+    const Other &)
+{
+}
+__device__ __forceinline__ bool wants_fields(const CompactArgs & C) { return C.use_fields != 0; }
+
+/* The columns of a finished ray the caller asked for (turtle_trace_fields), from the
+ * rows of the lane store: f = &store.f[0][tid], i = &store.i[0][tid], 128 apart. */
+__device__ __forceinline__ void store_fields(const CompactArgs & A, const double * f, const int * i)
+{
+        const unsigned long long ray = ((unsigned long long)(unsigned)i[I_RAYHI * 128] << 32) |
+            (unsigned long long)(unsigned)i[I_RAYLO * 128];
+#pragma unroll
+        for (int m = 0; m < TURTLE_TRACE_MEDIA; m++)
+                if (A.fields.length[m] != NULL) A.fields.length[m][ray] = f[(F_LEN + m) * 128];
+        if (A.fields.total != NULL) A.fields.total[ray] = f[F_TOTAL * 128];
+        if (A.fields.altitude != NULL) A.fields.altitude[ray] = f[F_ALT * 128];
+        if (A.fields.position != NULL) {
+                A.fields.position[3 * ray] = f[F_POS * 128];
+                A.fields.position[3 * ray + 1] = f[(F_POS + 1) * 128];
+                A.fields.position[3 * ray + 2] = f[(F_POS + 2) * 128];
+        }
+        if (A.fields.n_steps != NULL) A.fields.n_steps[ray] = i[I_NSTEPS * 128];
+        if (A.fields.status != NULL) A.fields.status[ray] = i[I_MEDIUM0 * 128];
+        if (A.fields.index != NULL) {
+                A.fields.index[2 * ray] = i[I_IDX0 * 128];
+                A.fields.index[2 * ray + 1] = i[I_IDX1 * 128];
+        }
+        if (A.fields.medium_hash != NULL) A.fields.medium_hash[ray] = (uint32_t)i[I_HASH * 128];
+        if (A.fields.n_changes != NULL) A.fields.n_changes[ray] = i[I_NCHANGES * 128];
+}
+
 /* The persistent ray-tracing kernel. MINB = CTAs of 128 threads per SM the register
  * allocation is bounded for (occupancy vs registers is a measured trade). */
-template <bool LLA, bool PROJ, int MINB, int SHAPE = tb::SHAPE_GENERIC, bool STREAM = false>
+template <bool LLA, bool PROJ, int MINB, int SHAPE = tb::SHAPE_GENERIC, bool STREAM = false,
+    bool COMPACT = false, int GATHER = GATHER_GLOBAL>
 __global__ void __launch_bounds__(128, MINB)
-    trace_kernel(const __grid_constant__ tb::Geometry G, const TraceArgs A)
+    trace_kernel(const __grid_constant__ tb::Geometry G, const TraceArgs A,
+        const typename ExtraOf<COMPACT, GATHER>::type C)
 {
         constexpr int NF = LLA ? N_F_LLA : N_F_BASE, NI = LLA ? N_I : N_I_BASE;
         __shared__ LaneStoreT<NF, NI> store;
@@ -187,6 +358,11 @@ __global__ void __launch_bounds__(128, MINB)
          * (sized by the transforms the geometry uses, tb::LlaView) */
         extern __shared__ double lla_store[];
         const tb::LlaView V = { lla_store + tid, 128 };
+        /* (GATHER_WINDOW: the DEM window of this CTA, staged once by the bulk copy engine) */
+        __shared__ __align__(128) uint16_t window[(GATHER == GATHER_WINDOW) ? WINDOW_NODES * WINDOW_NODES : 8];
+        __shared__ unsigned long long window_barrier;
+        NodesWindow from_window = { window, NULL, 0, 0, 0u };
+        window_setup(from_window, window, &window_barrier, C);
         unsigned my_steps = 0u, my_samples = 0u, my_rebuilds = 0u;
         constexpr bool LLA_COUNT = LLA;
         bool exhausted = false;
@@ -194,11 +370,9 @@ __global__ void __launch_bounds__(128, MINB)
         int owed = -1;             /* chunk whose completion count this lane still owes */
         unsigned iteration = 0u;
         unsigned long long t_wait = 0ull; /* STREAM: when this lane took its ticket */
-        int hold = 0; /* LLA, warp uniform: light iterations since the last heavy one */
-        constexpr int LIGHT_MIN = 5, HOLD_MAX = 24;
 
         for (;;) {
-                if (STREAM && ((++iteration & 127u) == 0u)) settle_done(A, owed);
+                if (STREAM && ((++iteration & 1023u) == 0u)) settle_done(A, owed);
                 /* ---- write out finished rays, one 96-byte record per instruction -------
                  * A finished lane has left its record in shared memory (MODE_DONE). Twelve
                  * lanes store its twelve 8-byte fields side by side: three full sectors in
@@ -206,31 +380,8 @@ __global__ void __launch_bounds__(128, MINB)
                  * the stores into a PEER's memory (multi-GPU) cheap
                  * on NVLink, where every request is a packet. */
                 unsigned done_mask = __ballot_sync(FULL, mode == MODE_DONE);
-                if ((done_mask != 0u) && A.use_fields && (mode == MODE_DONE)) {
-                        /* field arrays: the lane stores what the caller asked for itself */
-                        const unsigned long long ray =
-                            ((unsigned long long)(unsigned)SI(I_RAYHI) << 32) |
-                            (unsigned long long)(unsigned)SI(I_RAYLO);
-#pragma unroll
-                        for (int m = 0; m < TURTLE_TRACE_MEDIA; m++)
-                                if (A.fields.length[m] != NULL) A.fields.length[m][ray] = SF(F_LEN + m);
-                        if (A.fields.total != NULL) A.fields.total[ray] = SF(F_TOTAL);
-                        if (A.fields.altitude != NULL) A.fields.altitude[ray] = SF(F_ALT);
-                        if (A.fields.position != NULL) {
-                                A.fields.position[3 * ray] = SF(F_POS);
-                                A.fields.position[3 * ray + 1] = SF(F_POS + 1);
-                                A.fields.position[3 * ray + 2] = SF(F_POS + 2);
-                        }
-                        if (A.fields.n_steps != NULL) A.fields.n_steps[ray] = SI(I_NSTEPS);
-                        if (A.fields.status != NULL) A.fields.status[ray] = SI(I_MEDIUM0);
-                        if (A.fields.index != NULL) {
-                                A.fields.index[2 * ray] = SI(I_IDX0);
-                                A.fields.index[2 * ray + 1] = SI(I_IDX1);
-                        }
-                        if (A.fields.medium_hash != NULL)
-                                A.fields.medium_hash[ray] = (uint32_t)SI(I_HASH);
-                        if (A.fields.n_changes != NULL) A.fields.n_changes[ray] = SI(I_NCHANGES);
-                }
+                if (COMPACT && (done_mask != 0u) && wants_fields(C) && (mode == MODE_DONE))
+                        store_fields(C, &store.f[0][tid], &store.i[0][tid]); /* field arrays */
                 if (done_mask != 0u) __syncwarp(); /* the records are read across lanes */
                 const bool wrote = done_mask != 0u;
                 while (done_mask != 0u) {
@@ -240,7 +391,7 @@ __global__ void __launch_bounds__(128, MINB)
                         const unsigned long long ray =
                             ((unsigned long long)(unsigned)store.i[I_RAYHI][t] << 32) |
                             (unsigned long long)(unsigned)store.i[I_RAYLO][t];
-                        if ((lane < 12u) && (A.results != NULL)) {
+                        if ((lane < 12u) && (!COMPACT || (A.results != NULL))) {
                                 unsigned long long bits;
                                 if (lane < 9u) {
                                         const int row = (lane < 3u) ? (int)(F_POS + lane) :
@@ -317,25 +468,8 @@ __global__ void __launch_bounds__(128, MINB)
                                         const unsigned long long r =
                                             (A.order != NULL) ? A.order[q] : q;
                                         double pos[3], dir[3];
-                                        if (A.position == NULL) {
-                                                /* ray (i, j) of a fan: the products and sums of
-                                                 * turtle_ecef_from_horizontal, ecef.c:170-177 */
-                                                const unsigned long long per_band = A.fan_naz * A.fan_bundle;
-                                                const unsigned long long rr = r + A.fan_ray0;
-                                                const unsigned long long band = rr / per_band;
-                                                const unsigned long long rem = rr - band * per_band;
-                                                const unsigned long long i = rem / A.fan_bundle;
-                                                const unsigned long long j =
-                                                    band * A.fan_bundle + (rem - i * A.fan_bundle);
-                                                const double2 az = __ldg(A.fan_az + i);
-                                                const double2 el = __ldg(A.fan_el + j);
-                                                const double r0 = el.x * az.x, r1 = el.x * az.y, r2 = el.y;
-#pragma unroll
-                                                for (int c = 0; c < 3; c++) {
-                                                        pos[c] = A.fan_origin[c];
-                                                        dir[c] = r0 * A.fan_e[c] + r1 * A.fan_n[c] +
-                                                            r2 * A.fan_u[c];
-                                                }
+                                        if (COMPACT && (A.position == NULL)) {
+                                                fan_ray(C, r, pos, dir);
                                         } else {
                                                 /* (L2 loads: a streamed ray has just been written
                                                  * by a copy engine, L1 must not serve an older line) */
@@ -399,14 +533,13 @@ __global__ void __launch_bounds__(128, MINB)
                                 continue;
                         }
                 }
-                const bool active = !((mode == MODE_IDLE) || (mode == MODE_WAIT) || (mode == MODE_DONE));
-                if (!LLA && !active) continue;
+                if ((mode == MODE_IDLE) || (mode == MODE_WAIT) || (mode == MODE_DONE)) continue;
 
                 /* ---- exactly one ECEF -> geodetic transform per lane and iteration:
                  * the one of a geometry sample, or -- local approximation on -- one of
                  * the three finite-difference transforms of a Jacobian (stepper.c:144-162)
                  * that went stale when its reference point moved and that the coming
-                 * sample is about to apply (tb::lla_due; lazily: a Jacobian nobody reads
+                 * sample is about to apply (in range & stale; lazily: a Jacobian nobody reads
                  * is never built, see tb::get_geographic). Running the rebuild as
                  * iterations of its own keeps the lanes of a warp on equal work. */
                 tb::Sample S;
@@ -423,15 +556,21 @@ __global__ void __launch_bounds__(128, MINB)
                                 p[1] += SF(F_DIR + 1) * step;
                                 p[2] += SF(F_DIR + 2) * step;
                         }
-                        tb::sample_single_stack(G, p, S);
+                        if (GATHER == GATHER_PACKED)
+                                tb::sample_single_stack(tb::NodesPacked(), G, p, S);
+                        else if (GATHER == GATHER_WINDOW)
+                                tb::sample_single_stack(from_window, G, p, S);
+                        else
+                                tb::sample_single_stack(tb::NodesGlobal(), G, p, S);
                         moved[0] = p[0];
                         moved[1] = p[1];
                         moved[2] = p[2];
                 } else {
-                        double p[3] = { 0., 0., 0. };
+                        double p[3];
                         int rb_t = 0, rb_axis = 0;
                         bool heavy = true;
-                        if (active && (!LLA || (mode != MODE_REBUILD))) {
+                        unsigned in_range = 0u; /* LLA: transforms whose reference is in range */
+                        if (!LLA || (mode != MODE_REBUILD)) {
                                 double step = 0.; /* MODE_INIT: sample the start position */
                                 if (mode == MODE_TENT) /* stepper.c:824 */
                                         step = SF(F_DS);
@@ -445,8 +584,9 @@ __global__ void __launch_bounds__(128, MINB)
                                         p[1] += SF(F_DIR + 1) * step;
                                         p[2] += SF(F_DIR + 2) * step;
                                 }
-                                if (LLA) {
-                                        const unsigned due = tb::lla_due(G, V, (unsigned)SI(I_PEND), p);
+                                if (LLA) { /* the range tests of this sample, ONCE */
+                                        in_range = tb::lla_range_mask(G, V, p);
+                                        const unsigned due = in_range & (unsigned)SI(I_PEND);
                                         if (due != 0u) {
                                                 SI(I_RESUME) = mode;
                                                 SI(I_RB_MASK) = (int)due;
@@ -454,33 +594,6 @@ __global__ void __launch_bounds__(128, MINB)
                                                 mode = MODE_REBUILD;
                                         }
                                 }
-                        }
-                        if (LLA) {
-                                /* ---- light and heavy iterations. A sample in range of its
-                                 * reference points is LIGHT: no transform, no projection,
-                                 * a tenth of the instructions of the others (samples out of
-                                 * range, Jacobian columns). Near the ground, where the steps
-                                 * are shorter than the range, light samples come in long
-                                 * runs (a bisection is 23 of them) and are half of all
-                                 * samples -- one per iteration next to a heavy lane, each
-                                 * would cost its warp a heavy iteration. So while enough
-                                 * lanes are light the heavy ones sit the iteration out
-                                 * (bounded, so that none starves): the light runs are
-                                 * consumed at their own cost, and the heavy iterations
-                                 * that follow find most lanes heavy. Warp uniform. */
-                                const bool hv = active && ((mode == MODE_REBUILD) ||
-                                                              !tb::lla_all_in_range(G, V, p));
-                                const unsigned heavy_lanes = __ballot_sync(FULL, hv);
-                                const unsigned light_lanes = __ballot_sync(FULL, active && !hv);
-                                bool parked = false;
-                                if ((heavy_lanes != 0u) && (__popc(light_lanes) >= LIGHT_MIN) &&
-                                    (hold < HOLD_MAX)) {
-                                        hold++;
-                                        parked = hv;
-                                } else {
-                                        hold = 0;
-                                }
-                                if (!active || parked) continue;
                         }
                         if (LLA && (mode == MODE_REBUILD)) {
                                 rb_t = __ffs(SI(I_RB_MASK)) - 1;
@@ -492,8 +605,8 @@ __global__ void __launch_bounds__(128, MINB)
                                 if (rb_axis == 0) p[0] += 10.;
                                 else if (rb_axis == 1) p[1] += 10.;
                                 else p[2] += 10.;
-                        } else {
-                                heavy = tb::needs_geodetic<LLA>(G, V, p);
+                        } else if (LLA) {
+                                heavy = !((in_range >> G.lla_first) & 1u);
                         }
                         double pre[3] = { 0., 0., 0. };
                         if (heavy) tb::geodetic_with_geoid(G, p, pre);
@@ -519,7 +632,7 @@ __global__ void __launch_bounds__(128, MINB)
                                 stale = (unsigned)SI(I_PEND);
                         }
                         tb::sample_geometry<LLA, PROJ, true>(G, V, stale, last_pos,
-                            mode != MODE_BISECT, p, S, heavy ? pre : NULL);
+                            mode != MODE_BISECT, p, S, heavy ? pre : NULL, in_range);
                         if (LLA) {
                                 SI(I_PEND) = (int)stale;
                                 if (mode != MODE_BISECT) {
@@ -667,6 +780,11 @@ __global__ void __launch_bounds__(128, MINB)
                 atomicAdd(A.cursor + 1, steps64);
                 atomicAdd(A.cursor + 2, samples64);
                 if (LLA) atomicAdd(A.cursor + 4, rebuilds64);
+        }
+        if (GATHER == GATHER_WINDOW) {
+                unsigned long long hits64 = from_window.hits;
+                for (int o = 16; o > 0; o >>= 1) hits64 += __shfl_down_sync(FULL, hits64, o);
+                if (lane == 0u) atomicAdd(A.cursor + 5, hits64);
         }
 }
 
@@ -826,6 +944,7 @@ __global__ void __launch_bounds__(128, 5)
                 /* the position of the coming sample (none: idle lane, cached start sample,
                  * Jacobian column) */
                 double p[3] = { 0., 0., 0. };
+                unsigned in_range = 0u; /* LLA: transforms whose reference is in range */
                 const bool sampling = active && !started;
                 if (sampling && (!LLA || (mode != MODE_REBUILD))) {
                         double step = 0.;
@@ -841,8 +960,10 @@ __global__ void __launch_bounds__(128, 5)
                                 p[1] += SF(F_DIR + 1) * step;
                                 p[2] += SF(F_DIR + 2) * step;
                         }
-                        if (LLA) { /* a stale Jacobian about to be read? */
-                                const unsigned due = tb::lla_due(G, V, (unsigned)SI(I_PEND), p);
+                        if (LLA) { /* the range tests of this sample, ONCE; a stale Jacobian
+                                    * about to be read is rebuilt first */
+                                in_range = tb::lla_range_mask(G, V, p);
+                                const unsigned due = in_range & (unsigned)SI(I_PEND);
                                 if (due != 0u) {
                                         SI(I_RESUME) = mode;
                                         SI(I_RB_MASK) = (int)due;
@@ -851,9 +972,18 @@ __global__ void __launch_bounds__(128, 5)
                                 }
                         }
                 }
-                if (LLA) { /* light and heavy iterations: see trace_kernel (warp wide) */
+                if (LLA) {
+                        /* ---- light and heavy iterations (warp wide). A sample in range of
+                         * its reference points is LIGHT: no transform, no projection. One
+                         * step is a tentative sample and, on a medium change, a bisection of
+                         * 23 samples that are nearly all light: while enough lanes are in
+                         * such a run, the heavy ones (samples out of range, Jacobian columns)
+                         * sit the iteration out -- bounded, so that none starves -- and the
+                         * heavy iterations that follow find most lanes heavy. (Measured:
+                         * +10 % here; in the trace kernel, where light samples are spread
+                         * over the warps, the same policy costs 40 % and is not used.) */
                         const bool hv = sampling && ((mode == MODE_REBUILD) ||
-                                                        !tb::lla_all_in_range(G, V, p));
+                                                        (in_range != G.lla_mask));
                         const unsigned heavy_lanes = __ballot_sync(FULL, hv);
                         const unsigned light_lanes = __ballot_sync(FULL, active && !hv);
                         bool parked = false;
@@ -883,8 +1013,8 @@ __global__ void __launch_bounds__(128, 5)
                                         if (rb_axis == 0) p[0] += 10.;
                                         else if (rb_axis == 1) p[1] += 10.;
                                         else p[2] += 10.;
-                                } else {
-                                        heavy = tb::needs_geodetic<LLA>(G, V, p);
+                                } else if (LLA) {
+                                        heavy = !((in_range >> G.lla_first) & 1u);
                                 }
                                 double pre[3] = { 0., 0., 0. };
                                 if (heavy) tb::geodetic_with_geoid(G, p, pre);
@@ -905,7 +1035,7 @@ __global__ void __launch_bounds__(128, 5)
                                         SF(F_LASTPOS + 2) };
                                 unsigned stale = LLA ? (unsigned)SI(I_PEND) : 0u;
                                 tb::sample_geometry<LLA, PROJ, true>(G, V, stale, last_pos,
-                                    mode != MODE_BISECT, p, S, heavy ? pre : NULL);
+                                    mode != MODE_BISECT, p, S, heavy ? pre : NULL, in_range);
                                 if (LLA) SI(I_PEND) = (int)stale;
                                 if (mode != MODE_BISECT) {
                                         SF(F_LASTPOS) = last_pos[0];
@@ -1226,6 +1356,7 @@ __global__ void __launch_bounds__(256) projection_kernel(const tb::ProjDesc P, i
 
 /* ---- elevation kernels (ref: map.c:229-277) -------------------------------- */
 
+template <class Fetch>
 __global__ void __launch_bounds__(256) map_elevation_kernel(const tb::MapDesc M,
     unsigned long long n, const double * __restrict__ x, const double * __restrict__ y,
     double * __restrict__ z, int * __restrict__ inside)
@@ -1234,7 +1365,7 @@ __global__ void __launch_bounds__(256) map_elevation_kernel(const tb::MapDesc M,
         for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
              i < n; i += stride) {
                 double zi;
-                const int in = tb::map_elevation(M, x[i], y[i], zi);
+                const int in = tb::map_elevation(Fetch(), M, x[i], y[i], zi);
                 if (in) z[i] = zi;
                 if (inside != NULL) inside[i] = in;
         }
@@ -1258,8 +1389,32 @@ __global__ void __launch_bounds__(256) map_gradient_kernel(const tb::MapDesc M,
         }
 }
 
+/* ref: turtle_stack_gradient, stack.c:364-388, and turtle_stack_elevation, stack.c:338-361,
+ * on a stack of a plan (the resident tile table): outside -> 0 (stack.c:349-355,376-380) */
+__global__ void __launch_bounds__(256) stack_query_kernel(const __grid_constant__ tb::Geometry G,
+    int stack, int gradient, unsigned long long n, const double * __restrict__ latitude,
+    const double * __restrict__ longitude, double * __restrict__ a, double * __restrict__ b,
+    int * __restrict__ inside)
+{
+        const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+             i < n; i += stride) {
+                double u = 0., v = 0.;
+                int in;
+                if (gradient)
+                        in = tb::stack_gradient(G, G.stacks[stack], latitude[i], longitude[i], u, v);
+                else
+                        in = tb::stack_elevation(G, G.stacks[stack], latitude[i], longitude[i], u);
+                if (!in) u = v = 0.;
+                a[i] = u;
+                if (gradient) b[i] = v;
+                if (inside != NULL) inside[i] = in;
+        }
+}
+
 /* ECEF -> geodetic -> (projection) -> bilinear, fused: 24 B in, up to 36 B out
  * per point, nothing intermediate in HBM. */
+template <class Fetch>
 __global__ void __launch_bounds__(256) map_elevation_ecef_kernel(const tb::MapDesc M,
     const tb::ProjDesc P, unsigned long long n, const double * __restrict__ ecef,
     double * __restrict__ latitude, double * __restrict__ longitude,
@@ -1274,7 +1429,7 @@ __global__ void __launch_bounds__(256) map_elevation_ecef_kernel(const tb::MapDe
                 double mx = lo, my = la;
                 if (P.type != tb::PROJ_GEODETIC) tb::project(P, la, lo, mx, my);
                 double zi;
-                const int in = tb::map_elevation(M, mx, my, zi);
+                const int in = tb::map_elevation(Fetch(), M, mx, my, zi);
                 if (latitude != NULL) latitude[i] = la;
                 if (longitude != NULL) longitude[i] = lo;
                 if (altitude != NULL) altitude[i] = al;
@@ -1299,6 +1454,26 @@ __global__ void __launch_bounds__(256) ingest_kernel(uint16_t * __restrict__ dst
                 if (big_endian) v = (uint16_t)((v << 8) | (v >> 8));
                 const int oy = north_first ? ny - 1 - iy : iy;
                 dst[(size_t)oy * pitch + ix] = v;
+        }
+}
+
+/* The cell-packed copy of a grid (tb::NodesPacked): cell (ix, iy) = { z00, z10, z01, z11 } in
+ * ONE 8-byte word, same pitch as the grid; the last column / row of cells repeat the edge
+ * (never addressed: a query on the closed upper edge uses the cell before, map.c:256-265). */
+__global__ void __launch_bounds__(256) pack_cells_kernel(uint2 * __restrict__ cells,
+    const uint16_t * __restrict__ nodes, int pitch, int nx, int ny)
+{
+        const size_t total = (size_t)pitch * (size_t)ny;
+        const size_t stride = (size_t)gridDim.x * blockDim.x;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+                const int iy = (int)(i / (size_t)pitch);
+                const int ix = (int)(i - (size_t)iy * pitch);
+                const int jx = (ix + 1 < nx) ? ix + 1 : ((ix < nx) ? ix : nx - 1);
+                const int kx = (ix < nx) ? ix : nx - 1;
+                const int jy = (iy + 1 < ny) ? iy + 1 : iy;
+                const unsigned z00 = nodes[(size_t)iy * pitch + kx], z10 = nodes[(size_t)iy * pitch + jx];
+                const unsigned z01 = nodes[(size_t)jy * pitch + kx], z11 = nodes[(size_t)jy * pitch + jx];
+                cells[i] = make_uint2(z00 | (z10 << 16), z01 | (z11 << 16));
         }
 }
 
@@ -1437,6 +1612,13 @@ struct turtle_plan {
         /* device staging of the field arrays of a host-pointer call */
         void * d_field_pool;
         size_t field_pool_bytes;
+        /* node gathers of the single-stack trace kernel (turtle_plan_gather_set) */
+        int gather;
+        std::vector<tb::TileRec> h_tiles; /* the tile table as uploaded */
+        std::vector<tb::MapDesc> h_maps;  /* ... and the descriptors it refers to */
+        void * packed_pool;               /* cell-packed copies of the tiles */
+        tb::TileRec * d_tiles_packed;     /* tile table whose `nodes` are the packed copies */
+        WindowArgs window;
 };
 
 struct turtle_states {
@@ -1619,6 +1801,10 @@ static enum turtle_return freeze_plan(turtle_function_t * fn, struct turtle_step
         }
         plan->d_field_pool = NULL;
         plan->field_pool_bytes = 0;
+        plan->gather = GATHER_GLOBAL;
+        plan->packed_pool = NULL;
+        plan->d_tiles_packed = NULL;
+        memset(&plan->window, 0x0, sizeof plan->window);
         cudaDeviceProp prop;
         cudaGetDeviceProperties(&prop, device);
         plan->sm_count = prop.multiProcessorCount;
@@ -1712,6 +1898,8 @@ static enum turtle_return freeze_plan(turtle_function_t * fn, struct turtle_step
                 return tbh::raise(fn, TURTLE_RETURN_LIBRARY_ERROR, BATCH_CU, __LINE__,
                     "CUDA error while uploading the geometry: %s", cudaGetErrorString(err));
         }
+        plan->h_tiles = tiles;
+        plan->h_maps = maps;
         plan->G = F.G;
         plan->G.maps = plan->d_maps;
         plan->G.tiles = plan->d_tiles;
@@ -1826,6 +2014,8 @@ extern "C" void turtle_plan_destroy(struct turtle_plan ** plan_)
         cudaFree(plan->d_all_in);
         cudaFree(plan->d_all_out);
         cudaFree(plan->d_field_pool);
+        cudaFree(plan->packed_pool);
+        cudaFree(plan->d_tiles_packed);
         for (int k = 0; k < ALL_SLOTS; k++) {
                 if (plan->h_fan[k] != NULL) cudaFreeHost(plan->h_fan[k]);
                 cudaFree(plan->d_fan[k]);
@@ -1872,6 +2062,72 @@ extern "C" void turtle_plan_specialise_set(struct turtle_plan * plan, int enable
 extern "C" void turtle_plan_pipeline_set(struct turtle_plan * plan, int mode)
 {
         plan->pipeline_mode = mode;
+}
+
+/* How the single-stack trace kernel gathers its nodes (turtle_b200.h). */
+extern "C" enum turtle_return turtle_plan_gather_set(struct turtle_plan * plan, int mode,
+    double latitude, double longitude)
+{
+        turtle_function_t * fn = FN(&turtle_plan_gather_set);
+        if ((mode < GATHER_GLOBAL) || (mode > GATHER_WINDOW))
+                return tbh::raise(fn, TURTLE_RETURN_DOMAIN_ERROR, BATCH_CU, __LINE__,
+                    "invalid gather mode %d", mode);
+        if (mode == GATHER_GLOBAL) {
+                plan->gather = mode;
+                return TURTLE_RETURN_SUCCESS;
+        }
+        if (tb::geometry_shape(plan->G) != tb::SHAPE_STACK)
+                return tbh::raise(fn, TURTLE_RETURN_DOMAIN_ERROR, BATCH_CU, __LINE__,
+                    "packed / windowed gathers are for a geometry of one uniform stack");
+        CUDA_TRY(fn, cudaSetDevice(plan->device));
+        const tb::StackDesc & S = plan->G.stacks[0];
+        if ((mode == GATHER_PACKED) && (plan->d_tiles_packed == NULL)) {
+                /* a second, cell-packed copy of every tile: 4 x the bytes of the first */
+                const size_t per_tile = ((size_t)S.pitch * S.ny * sizeof(uint2) + 255) / 256 * 256;
+                size_t n_tiles = 0;
+                for (size_t i = 0; i < plan->h_tiles.size(); i++)
+                        if (plan->h_tiles[i].map >= 0) n_tiles++;
+                CUDA_TRY(fn, cudaMalloc(&plan->packed_pool, std::max<size_t>(per_tile * n_tiles, 256)));
+                std::vector<tb::TileRec> packed = plan->h_tiles;
+                size_t at = 0;
+                for (size_t i = 0; i < packed.size(); i++) {
+                        if (packed[i].map < 0) continue;
+                        uint2 * dst = (uint2 *)((char *)plan->packed_pool + at);
+                        pack_cells_kernel<<<plan->sm_count * 8, 256>>>(dst, packed[i].nodes, S.pitch,
+                            S.nx, S.ny);
+                        packed[i].nodes = (const uint16_t *)dst;
+                        at += per_tile;
+                }
+                CUDA_TRY(fn, cudaGetLastError());
+                CUDA_TRY(fn, cudaMalloc((void **)&plan->d_tiles_packed,
+                                 std::max<size_t>(packed.size(), 1) * sizeof(tb::TileRec)));
+                CUDA_TRY(fn, cudaMemcpy(plan->d_tiles_packed, packed.data(),
+                                 packed.size() * sizeof(tb::TileRec), cudaMemcpyHostToDevice));
+                CUDA_TRY(fn, cudaDeviceSynchronize());
+                plan->bytes += per_tile * n_tiles;
+        }
+        if (mode == GATHER_WINDOW) {
+                /* the window: WINDOW_NODES^2 nodes of the tile that holds (latitude,
+                 * longitude), centred there as far as the tile allows */
+                const int cx = (int)floor((longitude - S.lon0) / S.dlon);
+                const int cy = (int)floor((latitude - S.lat0) / S.dlat);
+                if ((cx < 0) || (cx >= S.nlon) || (cy < 0) || (cy >= S.nlat) ||
+                    (plan->h_tiles[S.tile0 + cy * S.nlon + cx].map < 0) ||
+                    (S.nx < WINDOW_NODES) || (S.ny < WINDOW_NODES))
+                        return tbh::raise(fn, TURTLE_RETURN_DOMAIN_ERROR, BATCH_CU, __LINE__,
+                            "no tile under the centre of the window");
+                const tb::TileRec & t = plan->h_tiles[S.tile0 + cy * S.nlon + cx];
+                int x0 = (int)((longitude - t.x0) / S.dx) - WINDOW_NODES / 2;
+                int y0 = (int)((latitude - t.y0) / S.dy) - WINDOW_NODES / 2;
+                x0 = std::max(0, std::min(x0, S.nx - WINDOW_NODES)) / 8 * 8;
+                y0 = std::max(0, std::min(y0, S.ny - WINDOW_NODES));
+                plan->window.tile = t.nodes;
+                plan->window.x0 = x0;
+                plan->window.y0 = y0;
+                plan->window.pitch = S.pitch;
+        }
+        plan->gather = mode;
+        return TURTLE_RETURN_SUCCESS;
 }
 
 /* Build the queue order of a launch (longest-expected-first) in plan->d_sched. */
@@ -1956,12 +2212,14 @@ static enum turtle_return check_rule(turtle_function_t * fn, const struct turtle
 /* Launch one instance of the trace kernel. The shared-memory carve-out is asked to be
  * just what the resident CTAs need: whatever they leave of the 256 kB is L1 for the DEM
  * gathers (the default heuristic takes the next larger configuration). */
-template <bool LLA, bool PROJ, int MINB, int SHAPE, bool STREAM = false>
+template <bool LLA, bool PROJ, int MINB, int SHAPE, bool STREAM = false, bool COMPACT = false,
+    int GATHER = GATHER_GLOBAL>
 static void trace_start(const struct turtle_plan * plan, int per_sm, int blocks, int threads,
-    cudaStream_t stream, const TraceArgs & A)
+    cudaStream_t stream, const TraceArgs & A, const typename ExtraOf<COMPACT, GATHER>::type & C)
 {
-        void (*kernel)(const tb::Geometry, const TraceArgs) =
-            trace_kernel<LLA, PROJ, MINB, SHAPE, STREAM>;
+        void (*kernel)(const tb::Geometry, const TraceArgs,
+            const typename ExtraOf<COMPACT, GATHER>::type) =
+            trace_kernel<LLA, PROJ, MINB, SHAPE, STREAM, COMPACT, GATHER>;
         const size_t dynamic = LLA ? lla_bytes(plan) : 0;
         static int carveout_of[16] = { 0 };
         static size_t dynamic_of[16] = { 0 };
@@ -1984,7 +2242,13 @@ static void trace_start(const struct turtle_plan * plan, int per_sm, int blocks,
                     (int)dynamic);
         cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
             carveout_of[key] - 1);
-        kernel<<<blocks, threads, dynamic, stream>>>(plan->G, A);
+        if (GATHER == GATHER_PACKED) { /* the tile table of the cell-packed copies */
+                tb::Geometry G = plan->G;
+                G.tiles = plan->d_tiles_packed;
+                kernel<<<blocks, threads, dynamic, stream>>>(G, A, C);
+                return;
+        }
+        kernel<<<blocks, threads, dynamic, stream>>>(plan->G, A, C);
 }
 
 /* Device-pointer calls are asynchronous: up to DEV_SLOTS of them may be in flight on a
@@ -2043,23 +2307,26 @@ static cudaError_t launch_trace(struct turtle_plan * plan, int slot, size_t n,
         if (err != cudaSuccess) return err;
         A.position = io.position;
         A.direction = io.direction;
+        CompactArgs C;
+        memset(&C, 0x0, sizeof C);
+        const NoCompactArgs none = { 0 };
         if (io.fan != NULL) {
                 A.position = A.direction = NULL;
-                A.fan_az = io.fan->az;
-                A.fan_el = io.fan->el;
+                C.fan_az = io.fan->az;
+                C.fan_el = io.fan->el;
                 for (int c = 0; c < 3; c++) {
-                        A.fan_origin[c] = io.fan->origin[c];
-                        A.fan_e[c] = io.fan->e[c];
-                        A.fan_n[c] = io.fan->n[c];
-                        A.fan_u[c] = io.fan->u[c];
+                        C.fan_origin[c] = io.fan->origin[c];
+                        C.fan_e[c] = io.fan->e[c];
+                        C.fan_n[c] = io.fan->n[c];
+                        C.fan_u[c] = io.fan->u[c];
                 }
-                A.fan_naz = io.fan->naz;
-                A.fan_bundle = io.fan->bundle;
-                A.fan_ray0 = io.fan->ray0;
+                C.fan_naz = io.fan->naz;
+                C.fan_bundle = io.fan->bundle;
+                C.fan_ray0 = io.fan->ray0;
         }
         A.results = io.results;
-        A.use_fields = (io.fields != NULL);
-        if (io.fields != NULL) A.fields = *io.fields;
+        C.use_fields = (io.fields != NULL);
+        if (io.fields != NULL) C.fields = *io.fields;
         A.cursor = d_counters;
         A.altitude_min = rule->altitude_min;
         A.altitude_max = rule->altitude_max;
@@ -2076,36 +2343,68 @@ static cudaError_t launch_trace(struct turtle_plan * plan, int slot, size_t n,
 #define TRACE_LAUNCH(MINB)                                                             \
         do {                                                                           \
                 if (proj)                                                              \
-                        trace_start<false, true, MINB, tb::SHAPE_GENERIC>(plan, per_sm, blocks, threads, stream, A); \
+                        trace_start<false, true, MINB, tb::SHAPE_GENERIC>(plan, per_sm, blocks, threads, stream, A, none); \
                 else                                                                   \
-                        trace_start<false, false, MINB, tb::SHAPE_GENERIC>(plan, per_sm, blocks, threads, stream, A); \
+                        trace_start<false, false, MINB, tb::SHAPE_GENERIC>(plan, per_sm, blocks, threads, stream, A, none); \
         } while (0)
         const int minb = per_sm * threads / 128;
         const bool stack_shape = plan->specialise && (tb::geometry_shape(plan->G) == tb::SHAPE_STACK);
-        if (streamed != NULL) {
+        const bool compact = (io.fan != NULL) || (io.fields != NULL);
+        if (compact) {
+                /* fan input and / or field outputs: the COMPACT kernels, at the default
+                 * residency of their shape */
+                const int sm6 = (per_sm < 6) ? per_sm : 6;
+                if (blocks > plan->sm_count * sm6) blocks = plan->sm_count * sm6;
+#define COMPACT_LAUNCH(STREAMED)                                                       \
+        do {                                                                           \
+                if (stack_shape)                                                       \
+                        trace_start<false, false, 6, tb::SHAPE_STACK, STREAMED, true>(plan, sm6, blocks, threads, stream, A, C); \
+                else if (lla && proj)                                                  \
+                        trace_start<true, true, 4, tb::SHAPE_GENERIC, STREAMED, true>(plan, sm6, blocks, threads, stream, A, C); \
+                else if (lla)                                                          \
+                        trace_start<true, false, 4, tb::SHAPE_GENERIC, STREAMED, true>(plan, sm6, blocks, threads, stream, A, C); \
+                else if (proj)                                                         \
+                        trace_start<false, true, 6, tb::SHAPE_GENERIC, STREAMED, true>(plan, sm6, blocks, threads, stream, A, C); \
+                else                                                                   \
+                        trace_start<false, false, 6, tb::SHAPE_GENERIC, STREAMED, true>(plan, sm6, blocks, threads, stream, A, C); \
+        } while (0)
+                if (streamed != NULL)
+                        COMPACT_LAUNCH(true);
+                else
+                        COMPACT_LAUNCH(false);
+#undef COMPACT_LAUNCH
+        } else if (streamed != NULL) {
                 /* streamed calls: the kernels waiting for their rays, 6 CTAs per SM */
                 const int cap = plan->sm_count * ((per_sm < 6) ? per_sm : 6);
                 if (blocks > cap) blocks = cap;
                 const int sm6 = (per_sm < 6) ? per_sm : 6;
                 if (stack_shape)
-                        trace_start<false, false, 6, tb::SHAPE_STACK, true>(plan, sm6, blocks, threads, stream, A);
+                        trace_start<false, false, 6, tb::SHAPE_STACK, true>(plan, sm6, blocks, threads, stream, A, none);
                 else if (lla && proj)
-                        trace_start<true, true, 4, tb::SHAPE_GENERIC, true>(plan, sm6, blocks, threads, stream, A);
+                        trace_start<true, true, 4, tb::SHAPE_GENERIC, true>(plan, sm6, blocks, threads, stream, A, none);
                 else if (lla)
-                        trace_start<true, false, 4, tb::SHAPE_GENERIC, true>(plan, sm6, blocks, threads, stream, A);
+                        trace_start<true, false, 4, tb::SHAPE_GENERIC, true>(plan, sm6, blocks, threads, stream, A, none);
                 else if (proj)
-                        trace_start<false, true, 6, tb::SHAPE_GENERIC, true>(plan, sm6, blocks, threads, stream, A);
+                        trace_start<false, true, 6, tb::SHAPE_GENERIC, true>(plan, sm6, blocks, threads, stream, A, none);
                 else
-                        trace_start<false, false, 6, tb::SHAPE_GENERIC, true>(plan, sm6, blocks, threads, stream, A);
+                        trace_start<false, false, 6, tb::SHAPE_GENERIC, true>(plan, sm6, blocks, threads, stream, A, none);
         } else if (lla && proj)
-                trace_start<true, true, 4, tb::SHAPE_GENERIC>(plan, per_sm, blocks, threads, stream, A);
+                trace_start<true, true, 4, tb::SHAPE_GENERIC>(plan, per_sm, blocks, threads, stream, A, none);
         else if (lla)
-                trace_start<true, false, 4, tb::SHAPE_GENERIC>(plan, per_sm, blocks, threads, stream, A);
+                trace_start<true, false, 4, tb::SHAPE_GENERIC>(plan, per_sm, blocks, threads, stream, A, none);
         else if (stack_shape) {
-                if (minb <= 6)
-                        trace_start<false, false, 6, tb::SHAPE_STACK>(plan, per_sm, blocks, threads, stream, A);
+                if ((minb <= 6) && (plan->gather == GATHER_PACKED))
+                        trace_start<false, false, 6, tb::SHAPE_STACK, false, false, GATHER_PACKED>(
+                            plan, per_sm, blocks, threads, stream, A, none);
+                else if ((minb <= 6) && (plan->gather == GATHER_WINDOW)) {
+                        WindowArgs W = plan->window;
+                        W.hits = d_counters;
+                        trace_start<false, false, 6, tb::SHAPE_STACK, false, false, GATHER_WINDOW>(
+                            plan, per_sm, blocks, threads, stream, A, W);
+                } else if (minb <= 6)
+                        trace_start<false, false, 6, tb::SHAPE_STACK>(plan, per_sm, blocks, threads, stream, A, none);
                 else
-                        trace_start<false, false, 8, tb::SHAPE_STACK>(plan, per_sm, blocks, threads, stream, A);
+                        trace_start<false, false, 8, tb::SHAPE_STACK>(plan, per_sm, blocks, threads, stream, A, none);
         } else if (minb <= 4)
                 TRACE_LAUNCH(4);
         else if (minb == 5)
@@ -2202,6 +2501,7 @@ extern "C" void turtle_plan_counters_sync(struct turtle_plan * plan)
                 plan->counters.steps = c[1];
                 plan->counters.samples = c[2];
                 plan->counters.rebuilds = c[4];
+                plan->counters.window_hits = c[5];
         }
 }
 
@@ -3175,6 +3475,7 @@ extern "C" void tb_map_release_mirrors(struct turtle_map * map)
                 if (map->mirrors[i].nodes == NULL) continue;
                 cudaSetDevice(map->mirrors[i].device);
                 cudaFree(map->mirrors[i].nodes);
+                cudaFree(map->mirrors[i].packed);
         }
         if (have) cudaSetDevice(current);
         map->mirrors.clear();
@@ -3182,7 +3483,7 @@ extern "C" void tb_map_release_mirrors(struct turtle_map * map)
 
 /* Device descriptor of `map` on the current device (uploads when stale). */
 static enum turtle_return map_mirror(turtle_function_t * fn, struct turtle_map * map,
-    tb::MapDesc * desc)
+    tb::MapDesc * desc, bool packed_ok = false)
 {
         enum turtle_return rc = require_current(fn);
         if (rc != TURTLE_RETURN_SUCCESS) return rc;
@@ -3208,6 +3509,19 @@ static enum turtle_return map_mirror(turtle_function_t * fn, struct turtle_map *
                 mirror->version = map->version;
         }
         desc->nodes = mirror->nodes;
+        if (packed_ok && (map->gather == 1)) { /* the cell-packed copy: one load per query */
+                if (mirror->packed == NULL)
+                        CUDA_TRY(fn, cudaMalloc(&mirror->packed,
+                                         (size_t)mirror->pitch * map->ny * sizeof(uint2)));
+                if (mirror->packed_version != map->version) {
+                        pack_cells_kernel<<<148 * 8, 256>>>((uint2 *)mirror->packed, mirror->nodes,
+                            mirror->pitch, map->nx, map->ny);
+                        CUDA_TRY(fn, cudaGetLastError());
+                        CUDA_TRY(fn, cudaDeviceSynchronize());
+                        mirror->packed_version = map->version;
+                }
+                desc->nodes = (const uint16_t *)mirror->packed;
+        }
         desc->nx = map->nx;
         desc->ny = map->ny;
         desc->pitch = mirror->pitch;
@@ -3226,12 +3540,23 @@ extern "C" enum turtle_return turtle_map_elevation_batch_device(struct turtle_ma
     size_t n, const double * x, const double * y, double * z, int * inside, void * stream)
 {
         tb::MapDesc M;
-        enum turtle_return rc = map_mirror(FN(&turtle_map_elevation_batch_device), map, &M);
+        enum turtle_return rc = map_mirror(FN(&turtle_map_elevation_batch_device), map, &M, true);
         if ((rc != TURTLE_RETURN_SUCCESS) || (n == 0)) return rc;
-        map_elevation_kernel<<<stream_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(
-            M, n, x, y, z, inside);
+        if (map->gather == 1)
+                map_elevation_kernel<tb::NodesPacked><<<stream_blocks(n, 256), 256, 0,
+                    (cudaStream_t)stream>>>(M, n, x, y, z, inside);
+        else
+                map_elevation_kernel<tb::NodesGlobal><<<stream_blocks(n, 256), 256, 0,
+                    (cudaStream_t)stream>>>(M, n, x, y, z, inside);
         CUDA_TRY(&turtle_map_elevation_batch_device, cudaGetLastError());
         return TURTLE_RETURN_SUCCESS;
+}
+
+/* 0: the batched elevation queries of `map` gather from its row-major mirror; 1: from a
+ * cell-packed second copy (turtle_b200.h). The gradient kernel always uses the first. */
+extern "C" void turtle_map_gather_set(struct turtle_map * map, int mode)
+{
+        map->gather = (mode == 1) ? 1 : 0;
 }
 
 extern "C" enum turtle_return turtle_map_elevation_batch(struct turtle_map * map, size_t n,
@@ -3294,12 +3619,16 @@ extern "C" enum turtle_return turtle_map_elevation_ecef_batch_device(struct turt
     double * z, int * inside, void * stream)
 {
         tb::MapDesc M;
-        enum turtle_return rc = map_mirror(FN(&turtle_map_elevation_ecef_batch_device), map, &M);
+        enum turtle_return rc = map_mirror(FN(&turtle_map_elevation_ecef_batch_device), map, &M, true);
         if ((rc != TURTLE_RETURN_SUCCESS) || (n == 0)) return rc;
         tb::ProjDesc P;
         tbh::projection_to_desc(turtle_map_projection(map), &P);
-        map_elevation_ecef_kernel<<<stream_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(
-            M, P, n, ecef, latitude, longitude, altitude, z, inside);
+        if (map->gather == 1)
+                map_elevation_ecef_kernel<tb::NodesPacked><<<stream_blocks(n, 256), 256, 0,
+                    (cudaStream_t)stream>>>(M, P, n, ecef, latitude, longitude, altitude, z, inside);
+        else
+                map_elevation_ecef_kernel<tb::NodesGlobal><<<stream_blocks(n, 256), 256, 0,
+                    (cudaStream_t)stream>>>(M, P, n, ecef, latitude, longitude, altitude, z, inside);
         CUDA_TRY(&turtle_map_elevation_ecef_batch_device, cudaGetLastError());
         return TURTLE_RETURN_SUCCESS;
 }
@@ -3329,6 +3658,74 @@ extern "C" enum turtle_return turtle_map_elevation_ecef_batch(struct turtle_map 
         DEV_BACK(&turtle_map_elevation_ecef_batch, z, d_z, n * sizeof(double));
         DEV_BACK(&turtle_map_elevation_ecef_batch, inside, d_in, n * sizeof(int));
         return TURTLE_RETURN_SUCCESS;
+}
+
+/* ---- stack queries on a plan ---------------------------------------------------------- */
+
+static enum turtle_return stack_query(turtle_function_t * fn, struct turtle_plan * plan, int stack,
+    int gradient, size_t n, const double * latitude, const double * longitude, double * a,
+    double * b, int * inside, bool on_device, void * stream)
+{
+        if ((stack < 0) || (stack >= plan->G.n_stacks))
+                return tbh::raise(fn, TURTLE_RETURN_DOMAIN_ERROR, BATCH_CU, __LINE__,
+                    "invalid stack index %d (the plan has %d)", stack, plan->G.n_stacks);
+        if (n == 0) return TURTLE_RETURN_SUCCESS;
+        CUDA_TRY(fn, cudaSetDevice(plan->device));
+        const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)plan->sm_count * 16);
+        if (on_device) {
+                stack_query_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(plan->G, stack, gradient,
+                    n, latitude, longitude, a, b, inside);
+                plan->counters.launches++;
+                CUDA_TRY(fn, cudaGetLastError());
+                return TURTLE_RETURN_SUCCESS;
+        }
+        DeviceBuffers B;
+        double *d_lat, *d_lon, *d_a, *d_b = NULL;
+        int * d_in;
+        DEV_IN(fn, B, d_lat, latitude, n * sizeof(double));
+        DEV_IN(fn, B, d_lon, longitude, n * sizeof(double));
+        DEV_OUT(fn, B, d_a, a, n * sizeof(double));
+        if (gradient) DEV_OUT(fn, B, d_b, b, n * sizeof(double));
+        DEV_OUT(fn, B, d_in, inside, n * sizeof(int));
+        stack_query_kernel<<<blocks, 256>>>(plan->G, stack, gradient, n, d_lat, d_lon, d_a, d_b, d_in);
+        plan->counters.launches++;
+        CUDA_TRY(fn, cudaGetLastError());
+        CUDA_TRY(fn, cudaDeviceSynchronize());
+        DEV_BACK(fn, a, d_a, n * sizeof(double));
+        if (gradient) DEV_BACK(fn, b, d_b, n * sizeof(double));
+        DEV_BACK(fn, inside, d_in, n * sizeof(int));
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_stack_gradient_batch(struct turtle_plan * plan, int stack,
+    size_t n, const double * latitude, const double * longitude, double * glat, double * glon,
+    int * inside)
+{
+        return stack_query(FN(&turtle_stack_gradient_batch), plan, stack, 1, n, latitude, longitude,
+            glat, glon, inside, false, NULL);
+}
+
+extern "C" enum turtle_return turtle_stack_gradient_batch_device(struct turtle_plan * plan,
+    int stack, size_t n, const double * latitude, const double * longitude, double * glat,
+    double * glon, int * inside, void * stream)
+{
+        return stack_query(FN(&turtle_stack_gradient_batch_device), plan, stack, 1, n, latitude,
+            longitude, glat, glon, inside, true, stream);
+}
+
+extern "C" enum turtle_return turtle_stack_elevation_batch(struct turtle_plan * plan, int stack,
+    size_t n, const double * latitude, const double * longitude, double * elevation, int * inside)
+{
+        return stack_query(FN(&turtle_stack_elevation_batch), plan, stack, 0, n, latitude,
+            longitude, elevation, NULL, inside, false, NULL);
+}
+
+extern "C" enum turtle_return turtle_stack_elevation_batch_device(struct turtle_plan * plan,
+    int stack, size_t n, const double * latitude, const double * longitude, double * elevation,
+    int * inside, void * stream)
+{
+        return stack_query(FN(&turtle_stack_elevation_batch_device), plan, stack, 0, n, latitude,
+            longitude, elevation, NULL, inside, true, stream);
 }
 
 /* ---- FP64 peak ------------------------------------------------------------------------ */
@@ -3421,6 +3818,8 @@ extern "C" int turtle_b200_kernel_info(const char * name, int * registers, int *
         if (strcmp(name, role) == 0) f = (const void *)(kernel)
         ROLE("trace_stack", (trace_kernel<false, false, 6, tb::SHAPE_STACK, false>));
         ROLE("trace_stack_stream", (trace_kernel<false, false, 6, tb::SHAPE_STACK, true>));
+        ROLE("trace_stack_compact", (trace_kernel<false, false, 6, tb::SHAPE_STACK, false, true>));
+        ROLE("trace_stack_stream_compact", (trace_kernel<false, false, 6, tb::SHAPE_STACK, true, true>));
         ROLE("trace", (trace_kernel<false, false, 6, tb::SHAPE_GENERIC, false>));
         ROLE("trace_proj", (trace_kernel<false, true, 6, tb::SHAPE_GENERIC, false>));
         ROLE("trace_lla", (trace_kernel<true, false, 4, tb::SHAPE_GENERIC, false>));
@@ -3430,8 +3829,10 @@ extern "C" int turtle_b200_kernel_info(const char * name, int * registers, int *
         ROLE("walk_lla", (walk_kernel<true, false>));
         ROLE("walk_lla_proj", (walk_kernel<true, true>));
         ROLE("to_geodetic", to_geodetic_kernel);
-        ROLE("map_elevation", map_elevation_kernel);
-        ROLE("map_elevation_ecef", map_elevation_ecef_kernel);
+        ROLE("map_elevation", map_elevation_kernel<tb::NodesGlobal>);
+        ROLE("map_elevation_ecef", map_elevation_ecef_kernel<tb::NodesGlobal>);
+        ROLE("map_elevation_packed", map_elevation_kernel<tb::NodesPacked>);
+        ROLE("map_elevation_ecef_packed", map_elevation_ecef_kernel<tb::NodesPacked>);
 #undef ROLE
         if (f == NULL) return -1;
         cudaFuncAttributes attr;
@@ -3480,6 +3881,11 @@ extern "C" const char * tb_batch_function_name(turtle_function_t * caller)
         NAME(turtle_stepper_trace_fan_device);
         NAME(turtle_stepper_trace_fields);
         NAME(turtle_stepper_trace_fields_device);
+        NAME(turtle_plan_gather_set);
+        NAME(turtle_stack_gradient_batch);
+        NAME(turtle_stack_gradient_batch_device);
+        NAME(turtle_stack_elevation_batch);
+        NAME(turtle_stack_elevation_batch_device);
         NAME(turtle_stepper_trace_crossings);
         NAME(turtle_stepper_trace_crossings_device);
         NAME(turtle_b200_peer_alloc);
