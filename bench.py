@@ -460,8 +460,8 @@ def main():
                "launches_per_step": hc["launches"],
                "api": "turtle_stepper_trace_fan: pinned host tables of %d azimuths + %d "
                       "elevations in, rock length (8 B) + status (4 B) + step count (4 B) per "
-                      "ray out to pinned host memory, drained in 256 Ki-ray pieces while the "
-                      "one persistent kernel runs" % (len(az_t), len(el_t))}
+                      "ray out to pinned host memory; up to 8 resident slices on two streams, the "
+                      "copy of a slice under the kernel of the next" % (len(az_t), len(el_t))}
         # the compact path against the full records of the same fan traced on the device
         d_chk = torch.empty((n_fan, 96), dtype=torch.uint8, device=dev)
         plan.trace_fan_device(fan_h, rule, results=d_chk, stream=stream.cuda_stream)

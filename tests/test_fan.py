@@ -92,14 +92,24 @@ def test_fields_only_and_rounds(small_stack):
     fan = tb.Plan.make_fan(lat, lon, origin, az, el, bundle=32)
     rec = np.zeros(n, dtype=tb.TRACE_RESULT)
     plan.trace_fan(fan, rule, results=rec)
+    # (the fan call cuts the fan in resident slices; the streamed kernel, in rounds, is the
+    # path of calls that stream rays in: held to the same answers here)
+    os.environ["TURTLE_B200_FAN_STREAMED"] = "1"
     os.environ["TURTLE_B200_STREAM_MAX_RAYS"] = str(1 << 18)  # three rounds
     two = tb.Plan.host_fields(n, ["length0", "status"])
     two["length0"][:] = -7.
     plan.trace_fan(fan, rule, fields=two)
-    del os.environ["TURTLE_B200_STREAM_MAX_RAYS"]
+    del os.environ["TURTLE_B200_STREAM_MAX_RAYS"], os.environ["TURTLE_B200_FAN_STREAMED"]
     assert np.array_equal(two["length0"], rec["length"][:, 0])
     assert np.array_equal(two["status"], rec["status"])
     assert plan.counters()["rays"] == n
+    two["length0"][:] = -7.
+    os.environ["TURTLE_B200_FAN_SLICE_RAYS"] = str(1 << 17)  # five slices on two streams
+    plan.trace_fan(fan, rule, fields=two)
+    del os.environ["TURTLE_B200_FAN_SLICE_RAYS"]
+    assert np.array_equal(two["length0"], rec["length"][:, 0])
+    c = plan.counters()
+    assert c["rays"] == n and c["steps"] == int(rec["n_steps"].sum())
     # arrays of rays in, fields out
     ora = sc.oracle()
     dirs = fan_rays(ora, lat, lon, az, el, 32)

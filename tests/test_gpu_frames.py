@@ -94,6 +94,19 @@ def test_map_elevation_bit_exact(ora):
     w2, _ = ora.map_elevation(m2, x[6:1000], y[6:1000])
     g2, _ = gm.elevation_batch(x[6:1000], y[6:1000])
     assert np.array_equal(w2, g2)
+    # the cell-packed copy of the grid (one 8-byte load per query): same bits, follows a
+    # re-fill, and the gradient kernel keeps reading the row-major mirror
+    from turtle_b200._lib import lib
+    lib.turtle_map_gather_set(gm.handle, 1)
+    w3, win3 = ora.map_elevation(m2, x, y)
+    g3, gin3 = gm.elevation_batch(x, y)
+    assert np.array_equal(win3, gin3) and np.array_equal(w3[win3 == 1], g3[gin3 == 1])
+    gm.fill(np.asarray(mp["values"]))
+    g4, gin4 = gm.elevation_batch(x, y)
+    assert np.array_equal(want_in, gin4) and np.array_equal(want_z[want_in == 1], g4[gin4 == 1])
+    wx, wy, wgin = ora.map_gradient(m, x[6:5000], y[6:5000])
+    gx, gy, ggin = gm.gradient_batch(x[6:5000], y[6:5000])
+    assert np.array_equal(wx, gx) and np.array_equal(wy, gy) and np.array_equal(wgin, ggin)
 
 
 def test_fused_ecef_elevation(ora):

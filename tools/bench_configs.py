@@ -71,12 +71,13 @@ def timed(fn, steps, warmup=3):
     return e0.elapsed_time(e1) / steps
 
 
-def trace_config(name, scene, pos, dirs, rule_o, rule_g, args, ops_per_sample, note):
+def trace_config(name, scene, pos, dirs, rule_o, rule_g, args, ops_per_sample, note, n_total=0):
     stepper, maps, stacks = scene.product()
     plan = stepper.freeze(LOCAL)
     plan.schedule_set(args.schedule)
-    n_job = len(pos)
-    if WORLD > 1:  # rays sharded with a stride (spreads the heavy tail), DEM replicated
+    n_job = n_total or len(pos)
+    if (WORLD > 1) and (len(pos) == n_job):
+        # rays sharded with a stride (spreads the heavy tail), DEM replicated
         pos, dirs = np.ascontiguousarray(pos[RANK::WORLD]), np.ascontiguousarray(dirs[RANK::WORLD])
     n = len(pos)
     d_pos, d_dir = torch.from_numpy(pos).to(DEV), torch.from_numpy(dirs).to(DEV)
@@ -208,24 +209,27 @@ def layered_scene(rg):
                  ops=[(H.ADD_FLAT, 0, 0.), (H.ADD_STACK, 0, 0.), (H.ADD_MAP, 0, 0.)], range=rg)
 
 
-def c3_inputs(n, rg):
+def c3_inputs(n, rg, rank=0, world=1):
     """Scene and rays of configuration 3: flat / 3 x 3 stack / Lambert map in one layer,
-    n random rays (origins in the stack box + 0.1 deg, isotropic directions)."""
+    n random rays (origins in the stack box + 0.1 deg, isotropic directions); with world > 1
+    only the strided shard rank, rank + world, ... of the n rays is generated."""
     scene = layered_scene(rg)
-    lat = B.STACK_LAT0 - 0.1 + (B.STACK_N + 0.2) * synth.random_uniform(n, 0xC3, 0)
-    lon = B.STACK_LON0 - 0.1 + (B.STACK_N + 0.2) * synth.random_uniform(n, 0xC3, 1)
-    alt = -500. + 5500. * synth.random_uniform(n, 0xC3, 2)
-    return scene, synth.np_ecef_from_geodetic(lat, lon, alt), synth.random_unit(n, 0xC3)
+    idx = np.arange(rank, n, world, dtype=np.uint64)
+    lat = B.STACK_LAT0 - 0.1 + (B.STACK_N + 0.2) * synth.random_uniform(n, 0xC3, 0, idx)
+    lon = B.STACK_LON0 - 0.1 + (B.STACK_N + 0.2) * synth.random_uniform(n, 0xC3, 1, idx)
+    alt = -500. + 5500. * synth.random_uniform(n, 0xC3, 2, idx)
+    return scene, synth.np_ecef_from_geodetic(lat, lon, alt), synth.random_unit(n, 0xC3, idx)
 
 
 def c3(args):
     n = args.rays or (1 << 26)  # BASELINE.json configs[2]: 64 Mi rays
-    scene, pos, dirs = c3_inputs(n, 10. if args.range is None else args.range)
+    scene, pos, dirs = c3_inputs(n, 10. if args.range is None else args.range, RANK, WORLD)
     trace_config("c3", scene, pos, dirs, H.rule(9000., length_max=1e5),
                  tb.trace_rule(9000., length_max=1e5), args, None,
                  "random rays (origins in the stack bbox + 0.1 deg, alt -500..5000 m, isotropic) "
                  "through flat(0) / 3x3 SRTMGL1 stack / 2001x2001 Lambert-93 map (5 m), range "
-                 "%g, stop leaves data | alt > 9000 m | path > 100 km | 1e5 steps" % scene.range)
+                 "%g, stop leaves data | alt > 9000 m | path > 100 km | 1e5 steps" % scene.range,
+                 n_total=n)
 
 
 def c4(args):
@@ -346,6 +350,7 @@ def c5(args):
     t0 = time.time()
     mp, row, col, (lon0, lat0, box) = c5_map(n_map)
     fill_s = time.time() - t0
+    lib.turtle_map_gather_set(mp.handle, args.gather)  # 1: cell-packed second copy
     n_job = args.rays or (1 << 30)
     n = n_job // WORLD  # a contiguous chunk of the points per rank
     gen = torch.Generator(device=DEV)
@@ -377,7 +382,7 @@ def c5(args):
         args.warmup)
     (ms_geo, _), (ms_map, _), (ms_fused, per_rank) = job_max(ms_geo), job_max(ms_map), job_max(ms_fused)
     if args.no_cpu:
-        emit({"config": "c5", "n_gpus": WORLD, "points": n_job, "ms_to_geodetic": ms_geo,
+        emit({"config": "c5", "gather": args.gather, "n_gpus": WORLD, "points": n_job, "ms_to_geodetic": ms_geo,
               "ms_map_elevation": ms_map, "ms_fused": ms_fused, "per_rank_ms_fused": per_rank,
               "Gpoints_per_s": {"to_geodetic": n_job / ms_geo / 1e6, "map_elevation": n_job / ms_map / 1e6,
                                 "fused": n_job / ms_fused / 1e6}})
@@ -425,17 +430,19 @@ def c5(args):
                         "bound": "fp64" if n * ops / ms / 1e9 / (dfma / 1e3) >
                         n * nbytes / ms / 1e6 / hbm else "hbm"})
         return out
+    packed = "_packed" if args.gather == 1 else ""
     line = {
         "config": "c5", "workload": "%d ECEF points (uniform over the map box + 0.05 deg, alt "
         "0-5000 m) -> turtle_ecef_to_geodetic_batch, turtle_map_elevation_batch and the fused "
         "kernel on a %dx%d uint16 geodetic map (%.0f MB)" % (n_job, n_map, n_map, n_map * n_map * 2 / 1e6),
-        "n_gpus": WORLD, "points": n_job, "points_per_gpu": n, "map_fill_seconds": fill_s,
+        "gather": args.gather, "n_gpus": WORLD, "points": n_job, "points_per_gpu": n,
+        "map_fill_seconds": fill_s,
         "to_geodetic": dict(ms=ms_geo, Gpoints_per_s=n_job / ms_geo / 1e6,
                             **roof(ms_geo, 48, "c5_to_geodetic")),
         "map_elevation": dict(ms=ms_map, Gpoints_per_s=n_job / ms_map / 1e6,
-                              **roof(ms_map, 36, "c5_map_elevation")),
+                              **roof(ms_map, 36, "c5_map_elevation" + packed)),
         "fused": dict(ms=ms_fused, Gpoints_per_s=n_job / ms_fused / 1e6,
-                      **roof(ms_fused, 68, "c5_map_elevation_ecef")),
+                      **roof(ms_fused, 68, "c5_map_elevation_ecef" + packed)),
         "peaks": {"hbm_GB_per_s": hbm, "fp64_Tinst_per_s": dfma / 1e3},
         "cpu_baseline": {"to_geodetic_Mpoints_per_s_1core": len(wla) / t_geo / 1e6,
                          "sample": "every %d-th point (%d points), 1 thread" % (stride, len(wla))},
@@ -460,6 +467,10 @@ def main():
     ap.add_argument("--map-nodes", type=int, default=20000)
     ap.add_argument("--schedule", type=int, default=0)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--l2-fetch", type=int, default=0,
+                    help="experiment: cudaLimitMaxL2FetchGranularity in bytes (32, 64, 128)")
+    ap.add_argument("--gather", type=int, default=0,
+                    help="c5: 1 = elevation queries gather from the cell-packed copy of the map")
     ap.add_argument("--inflight", type=int, default=0,
                     help="also measure the steady state with this many batches in flight")
     ap.add_argument("--max-steps", type=int, default=0,
@@ -469,6 +480,14 @@ def main():
     if args.config == "c1" and args.range is None:
         args.range = 0.
     torch.cuda.set_device(LOCAL)
+    if args.l2_fetch:
+        # experiment: the granularity at which an L2 miss fetches from HBM (a device limit,
+        # default 64 B on this GPU): random 2 x 2 gathers use 8 of the bytes they fetch
+        from cuda import cudart
+        torch.zeros(1, device=DEV)
+        err, = cudart.cudaDeviceSetLimit(cudart.cudaLimit.cudaLimitMaxL2FetchGranularity, args.l2_fetch)
+        err2, got = cudart.cudaDeviceGetLimit(cudart.cudaLimit.cudaLimitMaxL2FetchGranularity)
+        sys.stderr.write("cudaLimitMaxL2FetchGranularity: set %d -> %s, now %s\n" % (args.l2_fetch, err, got))
     if WORLD > 1:  # one process per GPU (torchrun): --rays is the size of the WHOLE job
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/turtle_b200_nccl.%h.%p.log")
         torch.distributed.init_process_group("nccl", device_id=torch.device(DEV))

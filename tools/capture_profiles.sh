@@ -12,6 +12,7 @@ O=gpurun_out
 run() { # name, kernel regex, launches to skip, command...
     name=$1; regex=$2; skip=$3; shift 3
     case ",$ONLY," in *",all,"*|*",$name,"*) ;; *) return;; esac
+    if [ "$(du -sm $O | cut -f1)" -gt 48 ]; then echo "$name: skipped, $O is near the 64 MiB that come back"; return; fi
     "$@" > $O/plain_${name}_$TAG.json 2> $O/plain_${name}_$TAG.err || { echo "$name: plain run failed"; return; }
     $NCU -k regex:$regex --launch-skip $skip -o $O/prof_${name}_$TAG "$@" > $O/ncu_${name}_$TAG.log 2>&1
     tail -1 $O/plain_${name}_$TAG.json | cut -c1-300
@@ -26,3 +27,5 @@ run c4_walk_proj walk_kernel 9 $BC --config c4 --range 0 --rays 4194304 --walk 6
 run c5_to_geodetic to_geodetic_kernel 1 $BC --config c5 --rays 268435456 --steps 1 --warmup 1 --no-cpu
 run c5_map_elevation "map_elevation_kernel" 1 $BC --config c5 --rays 268435456 --steps 1 --warmup 1 --no-cpu
 run c5_map_elevation_ecef map_elevation_ecef_kernel 1 $BC --config c5 --rays 268435456 --steps 1 --warmup 1 --no-cpu
+run c5_map_elevation_packed "map_elevation_kernel" 1 $BC --config c5 --gather 1 --rays 268435456 --steps 1 --warmup 1 --no-cpu
+run c5_map_elevation_ecef_packed map_elevation_ecef_kernel 1 $BC --config c5 --gather 1 --rays 268435456 --steps 1 --warmup 1 --no-cpu

@@ -370,6 +370,7 @@ __global__ void __launch_bounds__(128, MINB)
         int owed = -1;             /* chunk whose completion count this lane still owes */
         unsigned iteration = 0u;
         unsigned long long t_wait = 0ull; /* STREAM: when this lane took its ticket */
+        unsigned long long w_seen = 0ull; /* STREAM: the watermark as this lane saw it last */
 
         for (;;) {
                 if (STREAM && ((++iteration & 1023u) == 0u)) settle_done(A, owed);
@@ -447,8 +448,13 @@ __global__ void __launch_bounds__(128, MINB)
                                     (unsigned long long)(unsigned)SI(I_RAYLO);
                                 bool arrived = true;
                                 if (STREAM) {
-                                        const unsigned long long w =
-                                            *(const volatile unsigned long long *)A.watermark;
+                                        /* (the watermark only moves forward: it is read
+                                         * again only when what this lane saw last does not
+                                         * cover its ticket -- never, once a fan's tables or
+                                         * the last chunk are in) */
+                                        if (q >= w_seen)
+                                                w_seen = *(const volatile unsigned long long *)A.watermark;
+                                        const unsigned long long w = w_seen;
                                         arrived = q < w;
                                         if (w == STREAM_ABORT) {
                                                 mode = MODE_IDLE; /* the host gave up */
@@ -2835,6 +2841,113 @@ static enum turtle_return trace_rounds(turtle_function_t * fn, struct turtle_pla
         return TURTLE_RETURN_SUCCESS;
 }
 
+/* Host-pointer fan: nothing per ray goes in, so there is nothing to stream IN -- the fan is
+ * cut in up to 8 slices of consecutive rays (the lowest elevation bands, i.e. the longest
+ * rays, first), each a RESIDENT compact kernel followed by the copy of its records / field
+ * slices to the host, alternating on two streams: the copy of a slice runs under the
+ * kernel of the next, and the SMs that the tail of one slice leaves idle are taken by the
+ * head of the next (concurrent launches on one plan, see next_device_slot). Only the copy
+ * of the last slice is exposed. (The streamed kernel -- chunk flags, fences, a lane-side
+ * watermark -- does the same at 5 % more kernel time; it stays the path of calls that
+ * must stream rays in.) */
+static enum turtle_return trace_fan_sliced(turtle_function_t * fn, struct turtle_plan * plan,
+    size_t n, const struct turtle_fan * fan, size_t bundle, const struct turtle_trace_rule * rule,
+    struct turtle_trace_result * results, const struct turtle_trace_fields * fields)
+{
+        CUDA_TRY(fn, plan_pipeline(plan, 1)); /* the streams and their events */
+        if ((results != NULL) && (plan->all_records < n)) {
+                cudaFree(plan->d_all_out);
+                plan->d_all_out = NULL;
+                plan->all_records = 0;
+                CUDA_TRY(fn, cudaMalloc((void **)&plan->d_all_out, n * sizeof(turtle_trace_result)));
+                plan->all_records = n;
+        }
+        FieldSpec specs[12];
+        const int n_fields = (fields != NULL) ? field_specs(fields, specs) : 0;
+        char * d_field[12] = { NULL };
+        if (n_fields > 0) {
+                size_t need = 0;
+                for (int k = 0; k < n_fields; k++) need += (n * specs[k].bytes + 255) / 256 * 256;
+                if (plan->field_pool_bytes < need) {
+                        cudaFree(plan->d_field_pool);
+                        plan->d_field_pool = NULL;
+                        plan->field_pool_bytes = 0;
+                        CUDA_TRY(fn, cudaMalloc(&plan->d_field_pool, need));
+                        plan->field_pool_bytes = need;
+                }
+                size_t at = 0;
+                for (int k = 0; k < n_fields; k++) {
+                        d_field[k] = (char *)plan->d_field_pool + at;
+                        at += (n * specs[k].bytes + 255) / 256 * 256;
+                }
+        }
+        /* slices: whole bands of the fan (bundle x n_azimuth rays), about 2 Mi rays each */
+        const size_t band = std::max<size_t>(bundle * fan->n_azimuth, 1);
+        size_t slice_rays = (size_t)1 << 21;
+        if (getenv("TURTLE_B200_FAN_SLICE_RAYS") != NULL) { /* tests: several small slices */
+                const long long v = atoll(getenv("TURTLE_B200_FAN_SLICE_RAYS"));
+                if (v > 0) slice_rays = (size_t)v;
+        }
+        size_t n_slices = std::min<size_t>(DEV_SLOTS, std::max<size_t>(1, n / slice_rays));
+        size_t per_slice = (n / band + n_slices - 1) / n_slices * band;
+        if (per_slice == 0) per_slice = n;
+        n_slices = (n + per_slice - 1) / per_slice;
+        cudaStream_t lanes[2] = { plan->stream[0], plan->stream[1] };
+        FanTables tables;
+        CUDA_TRY(fn, fan_upload(plan, 0, fan, bundle, 0, lanes[0], &tables));
+        CUDA_TRY(fn, cudaEventRecord(plan->ev0[0], lanes[0]));
+        CUDA_TRY(fn, cudaStreamWaitEvent(lanes[1], plan->ev0[0], 0));
+        int slots[DEV_SLOTS];
+        plan->counters.launches = 0;
+        for (size_t k = 0; k < n_slices; k++) {
+                const size_t first = k * per_slice;
+                const size_t m = std::min(per_slice, n - first);
+                cudaStream_t st = lanes[k & 1];
+                FanTables slice = tables;
+                slice.ray0 = first;
+                struct turtle_trace_fields d_fields;
+                memset(&d_fields, 0x0, sizeof d_fields);
+                for (int f = 0; f < n_fields; f++)
+                        *(void **)((char *)&d_fields + specs[f].offset) =
+                            d_field[f] + first * specs[f].bytes;
+                const DeviceIo io = { NULL, NULL, &slice,
+                        (results != NULL) ? plan->d_all_out + first : NULL,
+                        (n_fields > 0) ? &d_fields : NULL };
+                slots[k] = next_device_slot(plan);
+                CUDA_TRY(fn, launch_trace(plan, slots[k], m, io, rule,
+                                 plan->d_counters + CTR * slots[k], st));
+                if (results != NULL)
+                        CUDA_TRY(fn, cudaMemcpyAsync(results + first, plan->d_all_out + first,
+                                         m * sizeof(turtle_trace_result), cudaMemcpyDeviceToHost, st));
+                for (int f = 0; f < n_fields; f++)
+                        CUDA_TRY(fn, cudaMemcpyAsync((char *)*specs[f].host + first * specs[f].bytes,
+                                         d_field[f] + first * specs[f].bytes, m * specs[f].bytes,
+                                         cudaMemcpyDeviceToHost, st));
+        }
+        CUDA_TRY(fn, cudaEventRecord(plan->ev1[0], lanes[0]));
+        CUDA_TRY(fn, cudaEventRecord(plan->ev1[1], lanes[1]));
+        CUDA_TRY(fn, cudaStreamSynchronize(lanes[0]));
+        CUDA_TRY(fn, cudaStreamSynchronize(lanes[1]));
+        float ms = 0.f, ms1 = 0.f; /* kernels + copies of both streams */
+        cudaEventElapsedTime(&ms, plan->ev0[0], plan->ev1[0]);
+        cudaEventElapsedTime(&ms1, plan->ev0[0], plan->ev1[1]);
+        if (ms1 > ms) ms = ms1;
+        const uint64_t launches = plan->counters.launches;
+        memset(&plan->counters, 0x0, sizeof(plan->counters));
+        for (size_t k = 0; k < n_slices; k++) {
+                unsigned long long c[CTR];
+                CUDA_TRY(fn, cudaMemcpy(c, plan->d_counters + CTR * slots[k], sizeof c,
+                                 cudaMemcpyDeviceToHost));
+                plan->counters.steps += c[1];
+                plan->counters.samples += c[2];
+                plan->counters.rebuilds += c[4];
+        }
+        plan->counters.rays = n;
+        plan->counters.launches = launches;
+        plan->counters.kernel_ms = ms;
+        return TURTLE_RETURN_SUCCESS;
+}
+
 extern "C" enum turtle_return turtle_stepper_trace_fan(struct turtle_plan * plan,
     const struct turtle_fan * fan, const struct turtle_trace_rule * rule,
     struct turtle_trace_result * results, const struct turtle_trace_fields * fields)
@@ -2848,7 +2961,9 @@ extern "C" enum turtle_return turtle_stepper_trace_fan(struct turtle_plan * plan
         memset(&plan->counters, 0x0, sizeof(plan->counters));
         if (n == 0) return TURTLE_RETURN_SUCCESS;
         CUDA_TRY(fn, cudaSetDevice(plan->device));
-        return trace_rounds(fn, plan, n, NULL, NULL, fan, bundle, rule, results, fields);
+        if (getenv("TURTLE_B200_FAN_STREAMED") != NULL) /* development: the streamed kernel */
+                return trace_rounds(fn, plan, n, NULL, NULL, fan, bundle, rule, results, fields);
+        return trace_fan_sliced(fn, plan, n, fan, bundle, rule, results, fields);
 }
 
 extern "C" enum turtle_return turtle_stepper_trace_fan_device(struct turtle_plan * plan,

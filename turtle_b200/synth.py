@@ -204,9 +204,10 @@ def golden_fan(n, el_min=0.5, el_max=30.0):
     return az, el
 
 
-def random_unit(n, seed):
-    """Isotropic unit vectors from a counter-based splitmix64 stream."""
-    k = np.arange(n, dtype=np.uint64)
+def random_unit(n, seed, index=None):
+    """Isotropic unit vectors from a counter-based splitmix64 stream (`index`: only those
+    elements of the n-element stream, e.g. the strided shard of one rank)."""
+    k = np.arange(n, dtype=np.uint64) if index is None else np.asarray(index, dtype=np.uint64)
     with np.errstate(over="ignore"):
         u1 = splitmix64(k * np.uint64(2) + np.uint64(seed) * np.uint64(0x1000003))
         u2 = splitmix64(k * np.uint64(2) + np.uint64(1) + np.uint64(seed) * np.uint64(0x1000003))
@@ -218,8 +219,8 @@ def random_unit(n, seed):
     return np.stack([sz * np.cos(ph), sz * np.sin(ph), cz], -1)
 
 
-def random_uniform(n, seed, stream=0):
-    k = np.arange(n, dtype=np.uint64)
+def random_uniform(n, seed, stream=0, index=None):
+    k = np.arange(n, dtype=np.uint64) if index is None else np.asarray(index, dtype=np.uint64)
     with np.errstate(over="ignore"):
         u = splitmix64(k + (np.uint64(seed) << np.uint64(20)) + (np.uint64(stream) << np.uint64(44)))
     return (u >> np.uint64(11)).astype(np.float64) / (1 << 53)
