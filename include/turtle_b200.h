@@ -98,11 +98,15 @@ struct turtle_plan_counters {
 /* ---- plans ---------------------------------------------------------------- */
 
 /* Threading: a plan carries the streams, staging buffers and counters of the calls made
- * through it -- ONE batch call at a time per plan (several plans, e.g. one per host thread
- * or per device, are independent; they share nothing but read-only tiles of their own).
- * This is the batched form of the reference's rule "one stepper per thread"
- * (include/turtle.h:141-149 of the reference). The `_device` variants are asynchronous on
- * the caller's stream; the host-pointer variants return when the results are in place. */
+ * through it. HOST-pointer calls (`*_batch`, `_trace_fan`, `_trace_fields`) return when their
+ * results are in place: ONE at a time per plan. DEVICE-pointer calls (`*_device`) are
+ * asynchronous on the caller's stream and up to 8 of them may be IN FLIGHT on one plan, each
+ * on its own stream, from one host thread: that is how a caller with several batches hides the
+ * tail of one (a launch ends when its slowest ray does) behind the head of the next --
+ * turtle_plan_counters_sync then reports the latest call. Several plans (one per host thread
+ * or per device) are independent; they share nothing but read-only tiles of their own. This
+ * is the batched form of the reference's rule "one stepper per thread"
+ * (include/turtle.h:141-149 of the reference). */
 
 /* Upload every map / tile referenced by `stepper` to `device` and flatten the
  * geometry. Stacks are made fully resident (all tiles of the grid are loaded):

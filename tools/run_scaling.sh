@@ -14,8 +14,8 @@ if [ "$N" -gt 1 ]; then
 else
     RUN="python"
 fi
-$RUN bench.py --gpus $N --steps 5 --warmup 3 --cpu-rays $([ "$N" -gt 1 ] && echo 0 || echo 4194304) >> $OUT 2>> $ERR
-BC="tools/bench_configs.py --no-cpu --steps 3"
+$RUN bench.py --gpus $N --steps 3 --warmup 3 --cpu-rays $([ "$N" -gt 1 ] && echo 0 || echo 4194304) >> $OUT 2>> $ERR
+BC="tools/bench_configs.py --no-cpu --steps 2"
 $RUN $BC --config c1 --range 0 >> $OUT 2>> $ERR
 $RUN $BC --config c1 --range 10 >> $OUT 2>> $ERR
 $RUN $BC --config c3 --range 0 --rays 67108864 >> $OUT 2>> $ERR

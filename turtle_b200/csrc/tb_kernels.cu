@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(128, MINB)
         /* local approximation: G.lla_rows columns of per-lane state in DYNAMIC shared memory
          * (sized by the transforms the geometry uses, tb::LlaView) */
         extern __shared__ double lla_store[];
-        const tb::LlaView V = { lla_store + tid, 128 };
+        const tb::LlaShared V = { lla_store + tid };
         /* (GATHER_WINDOW: the DEM window of this CTA, staged once by the bulk copy engine) */
         __shared__ __align__(128) uint16_t window[(GATHER == GATHER_WINDOW) ? WINDOW_NODES * WINDOW_NODES : 8];
         __shared__ unsigned long long window_barrier;
@@ -854,7 +854,22 @@ struct StepArgs {
  * particle that is done writes its outputs and state and its lane is refilled.
  * Step-granular lockstep (one thread = one whole step) would make every warp pay the
  * 23-sample bisection of its unluckiest lane on most steps. */
-template <bool LLA, bool PROJ>
+/* The local approximations of a particle: a column of the device states (STATES) or, when
+ * every particle starts from a reset stepper, of the kernel's shared scratch. */
+template <bool STATES> struct WalkView {
+        typedef tb::LlaShared type;
+};
+template <> struct WalkView<true> {
+        typedef tb::LlaGlobal type;
+};
+__device__ __forceinline__ void view_of_particle(tb::LlaGlobal & V, double * base, size_t stride)
+{
+        V.base = base;
+        V.stride = stride;
+}
+__device__ __forceinline__ void view_of_particle(tb::LlaShared &, double *, size_t) {}
+
+template <bool LLA, bool PROJ, bool STATES>
 __global__ void __launch_bounds__(128, 5)
     walk_kernel(const __grid_constant__ tb::Geometry G, const StepArgs A)
 {
@@ -867,7 +882,8 @@ __global__ void __launch_bounds__(128, 5)
 #define SI(k) store.i[k][tid]
 
         int mode = MODE_IDLE;
-        tb::LlaView V = { lla_store + tid, 128 };
+        typename WalkView<STATES>::type V;
+        V.base = lla_store + tid;
         unsigned my_steps = 0u, my_samples = 0u, my_rebuilds = 0u;
         bool exhausted = false;
         int hold = 0; /* LLA, warp uniform: light iterations since the last heavy one */
@@ -903,14 +919,15 @@ __global__ void __launch_bounds__(128, 5)
                                                 }
                                                 double lp[3] = { DBL_MAX, DBL_MAX, DBL_MAX };
                                                 SI(I_PEND) = 0;
-                                                if (A.states != NULL) {
+                                                if (STATES) {
                                                         const double * ps = A.states + r;
                                                         lp[0] = ps[(PS_LASTPOS + 0) * A.stride];
                                                         lp[1] = ps[(PS_LASTPOS + 1) * A.stride];
                                                         lp[2] = ps[(PS_LASTPOS + 2) * A.stride];
                                                         if (LLA) {
-                                                                V.base = A.states + PS_FIELDS * A.stride + r;
-                                                                V.stride = A.stride;
+                                                                view_of_particle(V,
+                                                                    A.states + PS_FIELDS * A.stride + r,
+                                                                    A.stride);
                                                                 SI(I_PEND) = __double2loint(
                                                                     ps[PS_STALE * A.stride]);
                                                         }
@@ -922,7 +939,7 @@ __global__ void __launch_bounds__(128, 5)
                                                 SF(F_LASTPOS + 2) = lp[2];
                                                 mode = MODE_INIT;
                                                 /* stepper.c:708-710: exact cache test */
-                                                if ((pos[0] == lp[0]) && (pos[1] == lp[1]) &&
+                                                if (STATES && (pos[0] == lp[0]) && (pos[1] == lp[1]) &&
                                                     (pos[2] == lp[2])) {
                                                         const double * ps = A.states + r;
                                                         SF(F_LAT) = ps[PS_LAT * A.stride];
@@ -1155,7 +1172,7 @@ __global__ void __launch_bounds__(128, 5)
                         A.index[2 * r] = idx0;
                         A.index[2 * r + 1] = SI(I_IDX1);
                 }
-                if (A.states != NULL) {
+                if (STATES) {
                         double * ps = A.states + r;
                         ps[(PS_LASTPOS + 0) * A.stride] = SF(F_LASTPOS);
                         ps[(PS_LASTPOS + 1) * A.stride] = SF(F_LASTPOS + 1);
@@ -1167,8 +1184,6 @@ __global__ void __launch_bounds__(128, 5)
                         ps[PS_ELEV1 * A.stride] = SF(F_ELEV1);
                         ps[PS_INDEX * A.stride] = __hiloint2double(SI(I_IDX1), idx0);
                         if (LLA) ps[PS_STALE * A.stride] = __hiloint2double(0, SI(I_PEND));
-                        V.base = lla_store + tid;
-                        V.stride = 128;
                 }
                 mode = MODE_IDLE;
         }
@@ -1200,7 +1215,7 @@ __global__ void states_reset_kernel(const __grid_constant__ tb::Geometry G, doub
                 for (int k = PS_LAT; k < PS_INDEX; k++) ps[k * stride] = 0.;
                 ps[PS_INDEX * stride] = __hiloint2double(-1, -1);
                 ps[PS_STALE * stride] = __hiloint2double(0, 0);
-                const tb::LlaView V = { states + PS_FIELDS * stride + i, (size_t)stride };
+                const tb::LlaGlobal V = { states + PS_FIELDS * stride + i, (size_t)stride };
                 tb::lla_reset(G, V);
         }
 }
@@ -3189,10 +3204,15 @@ extern "C" enum turtle_return turtle_stepper_step_batch_device(
                 if (plan->G.transforms[t].type != tb::PROJ_GEODETIC) proj = true;
         /* the 5 CTAs per SM get the carve-out they need and no more: the rest is L1 for the
          * DEM gathers (as for the trace kernel) */
-        void (*kernel)(const tb::Geometry, const StepArgs) =
-            (lla && proj) ? walk_kernel<true, true> :
-            (lla ? walk_kernel<true, false> :
-                   (proj ? walk_kernel<false, true> : walk_kernel<false, false>));
+        void (*kernel)(const tb::Geometry, const StepArgs);
+        if (states != NULL)
+                kernel = (lla && proj) ? walk_kernel<true, true, true> :
+                    (lla ? walk_kernel<true, false, true> :
+                           (proj ? walk_kernel<false, true, true> : walk_kernel<false, false, true>));
+        else
+                kernel = (lla && proj) ? walk_kernel<true, true, false> :
+                    (lla ? walk_kernel<true, false, false> :
+                           (proj ? walk_kernel<false, true, false> : walk_kernel<false, false, false>));
         /* the local approximations live in the device states, else (no states: every
          * particle starts from a reset stepper) in dynamic shared memory */
         const size_t dynamic = (lla && (states == NULL)) ? lla_bytes(plan) : 0;
@@ -3939,10 +3959,10 @@ extern "C" int turtle_b200_kernel_info(const char * name, int * registers, int *
         ROLE("trace_proj", (trace_kernel<false, true, 6, tb::SHAPE_GENERIC, false>));
         ROLE("trace_lla", (trace_kernel<true, false, 4, tb::SHAPE_GENERIC, false>));
         ROLE("trace_lla_proj", (trace_kernel<true, true, 4, tb::SHAPE_GENERIC, false>));
-        ROLE("walk", (walk_kernel<false, false>));
-        ROLE("walk_proj", (walk_kernel<false, true>));
-        ROLE("walk_lla", (walk_kernel<true, false>));
-        ROLE("walk_lla_proj", (walk_kernel<true, true>));
+        ROLE("walk", (walk_kernel<false, false, true>));
+        ROLE("walk_proj", (walk_kernel<false, true, true>));
+        ROLE("walk_lla", (walk_kernel<true, false, true>));
+        ROLE("walk_lla_proj", (walk_kernel<true, true, true>));
         ROLE("to_geodetic", to_geodetic_kernel);
         ROLE("map_elevation", map_elevation_kernel<tb::NodesGlobal>);
         ROLE("map_elevation_ecef", map_elevation_ecef_kernel<tb::NodesGlobal>);
