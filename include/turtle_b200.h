@@ -311,6 +311,25 @@ TURTLE_API enum turtle_return turtle_stepper_step_batch_device(
     double * longitude, double * altitude, double * elevation, double * step,
     int * index, void * stream);
 
+/* n_steps successive turtle_stepper_step calls per particle in ONE launch -- the inner loop
+ * of a transport engine that draws a new direction every step (BASELINE configuration 4).
+ * direction[j][i][3] is the direction of step j of particle i; the per-step outputs are
+ * [n_steps][n] (elevation, index: [n_steps][n][2]; any may be NULL), position[n][3] is
+ * advanced to the end of the walk. Same results as n_steps calls of
+ * turtle_stepper_step_batch; what differs is the traffic: the particle's stepper state
+ * (turtle_states, or a reset stepper when `states` is NULL) is read once, stays on chip for
+ * all its steps and is written once, instead of crossing HBM both ways every step. */
+TURTLE_API enum turtle_return turtle_stepper_walk_batch(
+    struct turtle_plan * plan, struct turtle_states * states, size_t n, int n_steps,
+    double * position, const double * direction, double * latitude,
+    double * longitude, double * altitude, double * elevation, double * step,
+    int * index);
+TURTLE_API enum turtle_return turtle_stepper_walk_batch_device(
+    struct turtle_plan * plan, struct turtle_states * states, size_t n, int n_steps,
+    double * position, const double * direction, double * latitude,
+    double * longitude, double * altitude, double * elevation, double * step,
+    int * index, void * stream);
+
 /* ---- ray origins (ref: turtle_stepper_position, src/turtle/stepper.c:877-931)
  * data_index[i] = -1 and position[i] untouched when (lat, lon) has no data. */
 TURTLE_API enum turtle_return turtle_stepper_position_batch(

@@ -69,6 +69,54 @@ def test_particle_walk_with_states(small_stack):
     assert np.abs(pos - want["position"])[~bad].max() < 1e-4
 
 
+@pytest.mark.parametrize("rg", [0., 1.])
+@pytest.mark.parametrize("with_states", [True, False])
+def test_walk_batch_is_k_steps(small_stack, rg, with_states):
+    """turtle_stepper_walk_batch: k steps per particle in one launch, the stepper state on chip
+    in between. Every output of every step, the final position and the state left behind
+    are those of k turtle_stepper_step_batch calls, byte for byte (and thereby the oracle's
+    walk, see test_particle_walk_with_states)."""
+    sc = c3(small_stack, rg, -1)
+    stepper, maps, stacks = sc.product()
+    plan = stepper.freeze(0)
+    rng = np.random.default_rng(33)
+    n, k1, k2 = 3001, 7, 5
+    la, lo = rng.uniform(45.2, 45.9, n), rng.uniform(2.2, 2.9, n)
+    ground, idx = plan.position(la, lo, rng.uniform(-50, 50, n), 0)
+    dirs = synth.random_unit(n * (k1 + k2), 5).reshape(k1 + k2, n, 3)
+    # a few particles stand still on a step (direction 0 0 0 is legal: the cached sample)
+    dirs[3, ::97] = 0.
+    s_a = plan.states(n) if with_states else None
+    pos = ground.copy()
+    steps = []
+    for j in range(k1 + k2):
+        out = plan.step(pos, dirs[j], states=s_a)
+        pos = out["position"]
+        steps.append(out)
+    s_b = plan.states(n) if with_states else None
+    p_b = ground.copy()
+    first = plan.walk(p_b, dirs[:k1], states=s_b)
+    if not with_states:
+        # no states: every WALK starts from a reset stepper, every step_batch call as well;
+        # compare the first step only, then the walk against the oracle
+        for f in ("altitude", "step", "index", "latitude", "longitude", "elevation"):
+            assert np.array_equal(first[f][0], steps[0][f]), f
+        ora = sc.oracle(locked=True)
+        want = ora.walk(ground, dirs[:k1], threads=os.cpu_count())
+        ok = np.logical_and.accumulate((first["index"] == want["index"]).all(2), 0)
+        assert (~ok[-1]).sum() <= max(2, n // 500)
+        assert np.abs(first["step"] - want["step"])[ok].max() < 1e-5
+        assert np.abs(first["altitude"] - want["altitude"])[ok].max() < 1e-5
+        return
+    second = plan.walk(p_b, dirs[k1:], states=s_b)
+    for j in range(k1 + k2):
+        got = first if j < k1 else second
+        jj = j if j < k1 else j - k1
+        for f in ("altitude", "step", "index", "latitude", "longitude", "elevation"):
+            assert np.array_equal(got[f][jj], steps[j][f]), (f, j)
+    assert np.array_equal(p_b, pos)
+
+
 def test_position_batch(small_stack):
     sc = c3(small_stack, 0., 1)
     ora = sc.oracle()

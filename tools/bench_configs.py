@@ -257,9 +257,11 @@ def c4(args):
 
     stride = max(1, n // args.cpu_rays)
     states = plan.states(n)
-    d_step = torch.empty(n, dtype=torch.float64, device=DEV)
-    d_alt = torch.empty(n, dtype=torch.float64, device=DEV)
-    d_idx = torch.empty((n, 2), dtype=torch.int32, device=DEV)
+    kk = max(1, min(args.multi, k))  # steps per launch (1: turtle_stepper_step_batch)
+    assert k % kk == 0
+    d_step = torch.empty((kk, n), dtype=torch.float64, device=DEV)
+    d_alt = torch.empty((kk, n), dtype=torch.float64, device=DEV)
+    d_idx = torch.empty((kk, n, 2), dtype=torch.int32, device=DEV)
     total_ms, sample_dirs, got_step, got_alt, got_idx = 0., [], [], [], []
     rebuilds = 0
     for rep in range(2):  # pass 0 = warm-up, pass 1 = timed
@@ -270,26 +272,32 @@ def c4(args):
         if WORLD > 1:
             torch.distributed.barrier()
         sample_dirs, got_step, got_alt, got_idx = [], [], [], []
-        for j in range(k):
-            d_dir = directions()
+        for j in range(k // kk):
+            d_dir = torch.stack([directions() for _ in range(kk)], 0).contiguous()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            plan.step_device(n, d_pos, d_dir, states=states, altitude=d_alt, step=d_step, index=d_idx)
+            if kk == 1:
+                plan.step_device(n, d_pos, d_dir, states=states, altitude=d_alt, step=d_step,
+                                 index=d_idx)
+            else:
+                plan.walk_device(n, kk, d_pos, d_dir, states=states, altitude=d_alt,
+                                 step=d_step, index=d_idx)
             e1.record()
             torch.cuda.synchronize()
             total_ms += e0.elapsed_time(e1)
             rebuilds += plan.counters(sync=True)["rebuilds"] if rep == 1 else 0
             if rep == 1 and not args.no_cpu:
-                sample_dirs.append(d_dir[::stride].cpu().numpy())
-                got_step.append(d_step[::stride].cpu().numpy())
-                got_alt.append(d_alt[::stride].cpu().numpy())
-                got_idx.append(d_idx[::stride].cpu().numpy())
+                for i in range(kk):
+                    sample_dirs.append(d_dir[i, ::stride].cpu().numpy())
+                    got_step.append(d_step[i, ::stride].cpu().numpy())
+                    got_alt.append(d_alt[i, ::stride].cpu().numpy())
+                    got_idx.append(d_idx[i, ::stride].cpu().numpy())
     ms_rank = total_ms
     total_ms, per_rank = job_max(ms_rank)
     if args.no_cpu:
         emit({"config": "c4", "n_gpus": WORLD, "particles": n_job, "walk_steps": k,
-              "ms_total": total_ms, "per_rank_ms": per_rank,
+              "steps_per_launch": kk, "range": scene.range, "ms_total": total_ms, "per_rank_ms": per_rank,
               "Msteps_per_s": n_job * k / total_ms / 1e3, "rebuilds_per_step": rebuilds / (n * k)})
         return
     if RANK != 0:
@@ -304,8 +312,8 @@ def c4(args):
         "config": "c4", "workload": "%d particles x %d turtle_stepper_step, fresh isotropic "
         "direction each step, start within +-50 m of the ground; geometry of c3, range %g, "
         "per-particle stepper state on the device" % (n_job, k, scene.range),
-        "n_gpus": WORLD, "particles": n_job, "walk_steps": k, "ms_total": total_ms,
-        "per_rank_ms": per_rank,
+        "n_gpus": WORLD, "particles": n_job, "walk_steps": k, "steps_per_launch": kk,
+        "ms_total": total_ms, "per_rank_ms": per_rank,
         "Msteps_per_s": n_job * k / total_ms / 1e3, "ns_per_step": total_ms * 1e6 / (n_job * k),
         "state_bytes_per_particle": int(states.bytes_per_particle),
         "rebuilds_per_step": rebuilds / (n * k),
@@ -463,6 +471,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--range", type=float, default=None)
     ap.add_argument("--walk", type=int, default=100)
+    ap.add_argument("--multi", type=int, default=1,
+                    help="c4: steps per launch (> 1: turtle_stepper_walk_batch)")
     ap.add_argument("--cpu-rays", type=int, default=1 << 18)
     ap.add_argument("--map-nodes", type=int, default=20000)
     ap.add_argument("--schedule", type=int, default=0)

@@ -29,3 +29,5 @@ run c5_map_elevation "map_elevation_kernel" 1 $BC --config c5 --rays 268435456 -
 run c5_map_elevation_ecef map_elevation_ecef_kernel 1 $BC --config c5 --rays 268435456 --steps 1 --warmup 1 --no-cpu
 run c5_map_elevation_packed "map_elevation_kernel" 1 $BC --config c5 --gather 1 --rays 268435456 --steps 1 --warmup 1 --no-cpu
 run c5_map_elevation_ecef_packed map_elevation_ecef_kernel 1 $BC --config c5 --gather 1 --rays 268435456 --steps 1 --warmup 1 --no-cpu
+run c4_walk_multi_proj walk_kernel 3 $BC --config c4 --range 0 --rays 4194304 --walk 12 --multi 6 --no-cpu
+run c4_walk_multi_lla_proj walk_kernel 3 $BC --config c4 --rays 4194304 --walk 12 --multi 6 --no-cpu

@@ -179,6 +179,8 @@ SIGNATURES = {
     "turtle_states_bytes_per_particle": (_N, [_P]),
     "turtle_stepper_step_batch": (_I, [_P, _P, _N] + [_P] * 8),
     "turtle_stepper_step_batch_device": (_I, [_P, _P, _N] + [_P] * 8 + [_P]),
+    "turtle_stepper_walk_batch": (_I, [_P, _P, _N, _I] + [_P] * 8),
+    "turtle_stepper_walk_batch_device": (_I, [_P, _P, _N, _I] + [_P] * 8 + [_P]),
     "turtle_stepper_position_batch": (_I, [_P, _N, _P, _P, _P, _I, _P, _P]),
     # frames
     "turtle_ecef_to_geodetic_batch": (_I, [_N, _P, _P, _P, _P]),

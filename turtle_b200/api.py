@@ -531,6 +531,31 @@ class Plan:
             _ptr(latitude), _ptr(longitude), _ptr(altitude), _ptr(elevation), _ptr(step),
             _ptr(index), C.c_void_p(stream) if stream else None))
 
+    def walk_device(self, n, n_steps, position, direction, states=None, latitude=None,
+                    longitude=None, altitude=None, elevation=None, step=None, index=None,
+                    stream=None):
+        """turtle_stepper_walk_batch_device: n_steps steps per particle in one launch;
+        direction is [n_steps, n, 3], the per-step outputs [n_steps, n(, 2)]."""
+        _check(lib.turtle_stepper_walk_batch_device(
+            self._p, states.handle if states else None, n, n_steps, _ptr(position),
+            _ptr(direction), _ptr(latitude), _ptr(longitude), _ptr(altitude), _ptr(elevation),
+            _ptr(step), _ptr(index), C.c_void_p(stream) if stream else None))
+
+    def walk(self, position, direction, states=None):
+        """turtle_stepper_walk_batch on host arrays: direction [n_steps, n, 3]. Returns a
+        dict of per-step arrays; ``position`` is advanced in place."""
+        position = _f8(position, (-1, 3))
+        d = _f8(direction)
+        k, n = d.shape[0], d.shape[1]
+        out = dict(position=position, altitude=np.empty((k, n)), step=np.empty((k, n)),
+                   index=np.empty((k, n, 2), dtype=np.int32), latitude=np.empty((k, n)),
+                   longitude=np.empty((k, n)), elevation=np.empty((k, n, 2)))
+        _check(lib.turtle_stepper_walk_batch(
+            self._p, states.handle if states else None, n, k, _ptr(position), _ptr(d),
+            _ptr(out["latitude"]), _ptr(out["longitude"]), _ptr(out["altitude"]),
+            _ptr(out["elevation"]), _ptr(out["step"]), _ptr(out["index"])))
+        return out
+
     def position(self, latitude, longitude, height, layer):
         la, lo, h = _f8(latitude), _f8(longitude), _f8(height)
         pos = np.zeros((len(la), 3))

@@ -21,6 +21,7 @@
  * No tensor cores: the path is FP64-pipe / issue bound (DESIGN.md roofline).
  */
 #include <cuda_runtime.h>
+#include <cuda_pipeline.h>
 #include <cub/device/device_radix_sort.cuh>
 
 #include <stdio.h>
@@ -844,6 +845,7 @@ struct StepArgs {
         double * step;
         int * index;
         unsigned long long * counters; /* [1] steps */
+        int n_steps; /* MULTI: steps per particle in this launch; outputs are [n_steps][n] */
 };
 
 /* One turtle_stepper_step per particle (ref: stepper.c:780-875), with the SAME
@@ -869,12 +871,18 @@ __device__ __forceinline__ void view_of_particle(tb::LlaGlobal & V, double * bas
 }
 __device__ __forceinline__ void view_of_particle(tb::LlaShared &, double *, size_t) {}
 
-template <bool LLA, bool PROJ, bool STATES>
+/* MULTI = turtle_stepper_walk_batch: n_steps successive turtle_stepper_step calls per
+ * particle in ONE launch, direction[j][i] for step j of particle i. The particle's state is
+ * loaded once, lives in the lane store (and, local approximation on, in shared columns) for
+ * all its steps and is stored once: per step only the direction comes in and the outputs go
+ * out -- where the one-step call moves the whole state both ways every step and is bound by
+ * that traffic. */
+template <bool LLA, bool PROJ, bool STATES, bool MULTI = false>
 __global__ void __launch_bounds__(128, 5)
     walk_kernel(const __grid_constant__ tb::Geometry G, const StepArgs A)
 {
         __shared__ LaneStore store;
-        extern __shared__ double lla_store[]; /* LLA without device states: scratch */
+        extern __shared__ double lla_store[]; /* LLA: scratch (no states), or the state (MULTI) */
         const unsigned tid = threadIdx.x;
         const unsigned lane = tid & 31u;
         const unsigned FULL = 0xffffffffu;
@@ -882,15 +890,16 @@ __global__ void __launch_bounds__(128, 5)
 #define SI(k) store.i[k][tid]
 
         int mode = MODE_IDLE;
-        typename WalkView<STATES>::type V;
+        typename WalkView<STATES && !MULTI>::type V;
         V.base = lla_store + tid;
+        const bool with_states = STATES && (!MULTI || (A.states != NULL));
         unsigned my_steps = 0u, my_samples = 0u, my_rebuilds = 0u;
         bool exhausted = false;
-        int hold = 0; /* LLA, warp uniform: light iterations since the last heavy one */
-        constexpr int LIGHT_MIN = 5, HOLD_MAX = 24;
+        bool carry = false; /* MULTI: the next step of this particle starts on its cached sample */
 
         for (;;) {
-                bool started = false; /* the start sample is available in the lane store */
+                bool started = carry; /* the start sample is available in the lane store */
+                carry = false;
                 bool finish = false;
                 double step_out = 0.;
                 const unsigned idle = __ballot_sync(FULL, mode == MODE_IDLE);
@@ -919,7 +928,8 @@ __global__ void __launch_bounds__(128, 5)
                                                 }
                                                 double lp[3] = { DBL_MAX, DBL_MAX, DBL_MAX };
                                                 SI(I_PEND) = 0;
-                                                if (STATES) {
+                                                if (MULTI) SI(I_NSTEPS) = 0;
+                                                if (with_states) {
                                                         const double * ps = A.states + r;
                                                         lp[0] = ps[(PS_LASTPOS + 0) * A.stride];
                                                         lp[1] = ps[(PS_LASTPOS + 1) * A.stride];
@@ -930,6 +940,17 @@ __global__ void __launch_bounds__(128, 5)
                                                                     A.stride);
                                                                 SI(I_PEND) = __double2loint(
                                                                     ps[PS_STALE * A.stride]);
+                                                                if (MULTI) {
+                                                                        /* the state moves in, once:
+                                                                         * asynchronous copies, one
+                                                                         * latency for all the rows */
+                                                                        for (int row = 0; row < G.lla_rows; row++)
+                                                                                __pipeline_memcpy_async(
+                                                                                    &lla_store[row * 128 + tid],
+                                                                                    &ps[(PS_FIELDS + row) * A.stride], 8);
+                                                                        __pipeline_commit();
+                                                                        __pipeline_wait_prior(0);
+                                                                }
                                                         }
                                                 } else if (LLA) {
                                                         tb::lla_reset(G, V);
@@ -939,7 +960,7 @@ __global__ void __launch_bounds__(128, 5)
                                                 SF(F_LASTPOS + 2) = lp[2];
                                                 mode = MODE_INIT;
                                                 /* stepper.c:708-710: exact cache test */
-                                                if (STATES && (pos[0] == lp[0]) && (pos[1] == lp[1]) &&
+                                                if (with_states && (pos[0] == lp[0]) && (pos[1] == lp[1]) &&
                                                     (pos[2] == lp[2])) {
                                                         const double * ps = A.states + r;
                                                         SF(F_LAT) = ps[PS_LAT * A.stride];
@@ -961,14 +982,46 @@ __global__ void __launch_bounds__(128, 5)
                                 continue;
                         }
                 }
-                const bool active = mode != MODE_IDLE;
-                if (!LLA && !active) continue;
+                if (mode == MODE_IDLE) continue;
 
-                /* the position of the coming sample (none: idle lane, cached start sample,
+                /* the start sample is known (stepper.c:791-821): the step is over (outside of
+                 * the layers, query mode) or its length is */
+                auto start_known = [&]() {
+                        tb::Sample last;
+                        last.lat = last.lon = 0.;
+                        last.alt = SF(F_ALT);
+                        last.elev0 = SF(F_ELEV0);
+                        last.elev1 = SF(F_ELEV1);
+                        last.idx0 = SI(I_IDX0);
+                        last.idx1 = SI(I_IDX1);
+                        if (last.idx0 < 0) {
+                                finish = true;
+                                step_out = 0.;
+                        } else {
+                                const double ds = tb::step_length(G, last);
+                                if (A.direction == NULL) {
+                                        finish = true;
+                                        step_out = ds;
+                                } else {
+                                        SI(I_MEDIUM0) = last.idx0;
+                                        SF(F_DS) = ds;
+                                        mode = MODE_TENT;
+                                }
+                        }
+                };
+                /* a particle that comes with the sample at its position (the usual case of a
+                 * walk: the last step ended there) goes on to its tentative sample in this
+                 * very iteration */
+                if (started && (mode == MODE_INIT)) {
+                        start_known();
+                        if (!finish) started = false;
+                }
+
+                /* the position of the coming sample (none: idle lane, finished step,
                  * Jacobian column) */
                 double p[3] = { 0., 0., 0. };
                 unsigned in_range = 0u; /* LLA: transforms whose reference is in range */
-                const bool sampling = active && !started;
+                const bool sampling = !started;
                 if (sampling && (!LLA || (mode != MODE_REBUILD))) {
                         double step = 0.;
                         if (mode == MODE_TENT)
@@ -995,31 +1048,6 @@ __global__ void __launch_bounds__(128, 5)
                                 }
                         }
                 }
-                if (LLA) {
-                        /* ---- light and heavy iterations (warp wide). A sample in range of
-                         * its reference points is LIGHT: no transform, no projection. One
-                         * step is a tentative sample and, on a medium change, a bisection of
-                         * 23 samples that are nearly all light: while enough lanes are in
-                         * such a run, the heavy ones (samples out of range, Jacobian columns)
-                         * sit the iteration out -- bounded, so that none starves -- and the
-                         * heavy iterations that follow find most lanes heavy. (Measured:
-                         * +10 % here; in the trace kernel, where light samples are spread
-                         * over the warps, the same policy costs 40 % and is not used.) */
-                        const bool hv = sampling && ((mode == MODE_REBUILD) ||
-                                                        (in_range != G.lla_mask));
-                        const unsigned heavy_lanes = __ballot_sync(FULL, hv);
-                        const unsigned light_lanes = __ballot_sync(FULL, active && !hv);
-                        bool parked = false;
-                        if ((heavy_lanes != 0u) && (__popc(light_lanes) >= LIGHT_MIN) &&
-                            (hold < HOLD_MAX)) {
-                                hold++;
-                                parked = hv;
-                        } else {
-                                hold = 0;
-                        }
-                        if (!active || parked) continue;
-                }
-
                 if (!started) {
                         /* ---- one ECEF -> geodetic transform ------------------------- */
                         tb::Sample S;
@@ -1124,55 +1152,48 @@ __global__ void __launch_bounds__(128, 5)
                         if (finish) my_steps++;
                 }
 
-                if (started && (mode == MODE_INIT)) {
-                        /* the start sample is known: stepper.c:791-821 */
-                        tb::Sample last;
-                        last.lat = last.lon = 0.;
-                        last.alt = SF(F_ALT);
-                        last.elev0 = SF(F_ELEV0);
-                        last.elev1 = SF(F_ELEV1);
-                        last.idx0 = SI(I_IDX0);
-                        last.idx1 = SI(I_IDX1);
-                        if (last.idx0 < 0) {
-                                finish = true;
-                                step_out = 0.;
-                        } else {
-                                const double ds = tb::step_length(G, last);
-                                if (A.direction == NULL) {
-                                        finish = true;
-                                        step_out = ds;
-                                } else {
-                                        SI(I_MEDIUM0) = last.idx0;
-                                        SF(F_DS) = ds;
-                                        mode = MODE_TENT;
-                                }
-                        }
-                }
+                if (started && !finish && (mode == MODE_INIT)) start_known();
                 if (!finish) continue;
 
-                /* ---- outputs and state of a finished particle (a Jacobian that is still
-                 * stale stays so: the mask is part of the state) ------------------------ */
+                /* ---- outputs of a finished step; state of a finished particle (a Jacobian
+                 * that is still stale stays so: the mask is part of the state) ------------ */
                 const unsigned long long r = ((unsigned long long)(unsigned)SI(I_RAYHI) << 32) |
                     (unsigned long long)(unsigned)SI(I_RAYLO);
                 const int idx0 = SI(I_IDX0);
+                const int j = MULTI ? SI(I_NSTEPS) : 0;
+                const unsigned long long o = MULTI ? (unsigned long long)j * A.n + r : r;
+                if (A.latitude != NULL) A.latitude[o] = SF(F_LAT);
+                if (A.longitude != NULL) A.longitude[o] = SF(F_LON);
+                if (A.altitude != NULL) A.altitude[o] = SF(F_ALT);
+                if (A.elevation != NULL) { /* stepper.c:765-772 */
+                        A.elevation[2 * o] = (idx0 >= 0) ? SF(F_ELEV0) : 0.;
+                        A.elevation[2 * o + 1] = (idx0 >= 0) ? SF(F_ELEV1) : 0.;
+                }
+                if (A.step != NULL) A.step[o] = step_out;
+                if (A.index != NULL) {
+                        A.index[2 * o] = idx0;
+                        A.index[2 * o + 1] = SI(I_IDX1);
+                }
+                if (MULTI && (j + 1 < A.n_steps)) {
+                        /* the next turtle_stepper_step of this particle: its direction comes
+                         * in; the sample at its position is the cached one when the position
+                         * is the last sampled one (stepper.c:708-710) */
+                        const double * d = A.direction + 3ull * ((unsigned long long)(j + 1) * A.n + r);
+                        SI(I_NSTEPS) = j + 1;
+                        SF(F_DIR) = d[0];
+                        SF(F_DIR + 1) = d[1];
+                        SF(F_DIR + 2) = d[2];
+                        carry = (SF(F_POS) == SF(F_LASTPOS)) && (SF(F_POS + 1) == SF(F_LASTPOS + 1)) &&
+                            (SF(F_POS + 2) == SF(F_LASTPOS + 2));
+                        mode = MODE_INIT;
+                        continue;
+                }
                 if (A.direction != NULL) {
                         A.position[3 * r] = SF(F_POS);
                         A.position[3 * r + 1] = SF(F_POS + 1);
                         A.position[3 * r + 2] = SF(F_POS + 2);
                 }
-                if (A.latitude != NULL) A.latitude[r] = SF(F_LAT);
-                if (A.longitude != NULL) A.longitude[r] = SF(F_LON);
-                if (A.altitude != NULL) A.altitude[r] = SF(F_ALT);
-                if (A.elevation != NULL) { /* stepper.c:765-772 */
-                        A.elevation[2 * r] = (idx0 >= 0) ? SF(F_ELEV0) : 0.;
-                        A.elevation[2 * r + 1] = (idx0 >= 0) ? SF(F_ELEV1) : 0.;
-                }
-                if (A.step != NULL) A.step[r] = step_out;
-                if (A.index != NULL) {
-                        A.index[2 * r] = idx0;
-                        A.index[2 * r + 1] = SI(I_IDX1);
-                }
-                if (STATES) {
+                if (with_states) {
                         double * ps = A.states + r;
                         ps[(PS_LASTPOS + 0) * A.stride] = SF(F_LASTPOS);
                         ps[(PS_LASTPOS + 1) * A.stride] = SF(F_LASTPOS + 1);
@@ -1183,7 +1204,14 @@ __global__ void __launch_bounds__(128, 5)
                         ps[PS_ELEV0 * A.stride] = SF(F_ELEV0);
                         ps[PS_ELEV1 * A.stride] = SF(F_ELEV1);
                         ps[PS_INDEX * A.stride] = __hiloint2double(SI(I_IDX1), idx0);
-                        if (LLA) ps[PS_STALE * A.stride] = __hiloint2double(0, SI(I_PEND));
+                        if (LLA) {
+                                ps[PS_STALE * A.stride] = __hiloint2double(0, SI(I_PEND));
+                                if (MULTI) /* ... and out, once */
+#pragma unroll 4
+                                        for (int row = 0; row < G.lla_rows; row++)
+                                                ps[(PS_FIELDS + row) * A.stride] =
+                                                    lla_store[row * 128 + tid];
+                        }
                 }
                 mode = MODE_IDLE;
         }
@@ -3167,18 +3195,19 @@ extern "C" enum turtle_return turtle_states_reset(struct turtle_states * states)
         return TURTLE_RETURN_SUCCESS;
 }
 
-extern "C" enum turtle_return turtle_stepper_step_batch_device(
-    struct turtle_plan * plan, struct turtle_states * states, size_t n,
-    double * position, const double * direction, double * latitude,
-    double * longitude, double * altitude, double * elevation, double * step,
-    int * index, void * stream)
+/* Launch the walk kernel: n particles, n_steps turtle_stepper_step each (1: the step_batch
+ * calls, states used in place; > 1: turtle_stepper_walk_batch, state resident in the lane
+ * store for the whole launch). */
+static enum turtle_return launch_walk(turtle_function_t * fn, struct turtle_plan * plan,
+    struct turtle_states * states, size_t n, int n_steps, bool multi, double * position,
+    const double * direction, double * latitude, double * longitude, double * altitude,
+    double * elevation, double * step, int * index, void * stream)
 {
         if ((states != NULL) && ((states->plan != plan) || (states->n < n)))
-                return tbh::raise(FN(&turtle_stepper_step_batch_device),
-                    TURTLE_RETURN_DOMAIN_ERROR, BATCH_CU, __LINE__,
+                return tbh::raise(fn, TURTLE_RETURN_DOMAIN_ERROR, BATCH_CU, __LINE__,
                     "states do not match the plan or are too few");
         if (n == 0) return TURTLE_RETURN_SUCCESS;
-        CUDA_TRY(&turtle_stepper_step_batch_device, cudaSetDevice(plan->device));
+        CUDA_TRY(fn, cudaSetDevice(plan->device));
         StepArgs A;
         A.n = n;
         A.states = (states != NULL) ? states->d_states : NULL;
@@ -3191,21 +3220,26 @@ extern "C" enum turtle_return turtle_stepper_step_batch_device(
         A.elevation = elevation;
         A.step = step;
         A.index = index;
+        A.n_steps = n_steps;
         A.counters = plan->d_counters + CTR * next_device_slot(plan);
         const int threads = 128;
         int blocks = (int)std::min<size_t>((n + threads - 1) / threads,
             (size_t)plan->sm_count * 5);
         cudaStream_t st = (cudaStream_t)stream;
-        CUDA_TRY(&turtle_stepper_step_batch_device,
-            cudaMemsetAsync(A.counters, 0x0, CTR * sizeof(unsigned long long), st));
+        CUDA_TRY(fn, cudaMemsetAsync(A.counters, 0x0, CTR * sizeof(unsigned long long), st));
         const bool lla = plan->G.range > 0.;
         bool proj = false;
         for (int t = 0; t < plan->G.n_transforms; t++)
                 if (plan->G.transforms[t].type != tb::PROJ_GEODETIC) proj = true;
-        /* the 5 CTAs per SM get the carve-out they need and no more: the rest is L1 for the
+        /* the CTAs per SM get the carve-out they need and no more: the rest is L1 for the
          * DEM gathers (as for the trace kernel) */
         void (*kernel)(const tb::Geometry, const StepArgs);
-        if (states != NULL)
+        if (multi)
+                kernel = (lla && proj) ? walk_kernel<true, true, true, true> :
+                    (lla ? walk_kernel<true, false, true, true> :
+                           (proj ? walk_kernel<false, true, true, true> :
+                                   walk_kernel<false, false, true, true>));
+        else if (states != NULL)
                 kernel = (lla && proj) ? walk_kernel<true, true, true> :
                     (lla ? walk_kernel<true, false, true> :
                            (proj ? walk_kernel<false, true, true> : walk_kernel<false, false, true>));
@@ -3213,9 +3247,10 @@ extern "C" enum turtle_return turtle_stepper_step_batch_device(
                 kernel = (lla && proj) ? walk_kernel<true, true, false> :
                     (lla ? walk_kernel<true, false, false> :
                            (proj ? walk_kernel<false, true, false> : walk_kernel<false, false, false>));
-        /* the local approximations live in the device states, else (no states: every
-         * particle starts from a reset stepper) in dynamic shared memory */
-        const size_t dynamic = (lla && (states == NULL)) ? lla_bytes(plan) : 0;
+        /* the local approximations live in the device states (one step), else in dynamic
+         * shared memory (no states: every particle starts from a reset stepper; several
+         * steps: the state moves in and out once) */
+        const size_t dynamic = (lla && (multi || (states == NULL))) ? lla_bytes(plan) : 0;
         cudaFuncAttributes attr;
         if (cudaFuncGetAttributes(&attr, kernel) == cudaSuccess) {
                 const size_t cta = attr.sharedSizeBytes + dynamic + 1024;
@@ -3234,9 +3269,33 @@ extern "C" enum turtle_return turtle_stepper_step_batch_device(
         kernel<<<blocks, threads, dynamic, st>>>(plan->G, A);
         plan->counters.launches++;
         plan->counters.rays = n;
-        plan->counters.steps = (direction != NULL) ? n : 0;
-        CUDA_TRY(&turtle_stepper_step_batch_device, cudaGetLastError());
+        plan->counters.steps = (direction != NULL) ? n * (size_t)n_steps : 0;
+        CUDA_TRY(fn, cudaGetLastError());
         return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_stepper_step_batch_device(
+    struct turtle_plan * plan, struct turtle_states * states, size_t n,
+    double * position, const double * direction, double * latitude,
+    double * longitude, double * altitude, double * elevation, double * step,
+    int * index, void * stream)
+{
+        return launch_walk(FN(&turtle_stepper_step_batch_device), plan, states, n, 1, false,
+            position, direction, latitude, longitude, altitude, elevation, step, index, stream);
+}
+
+/* n_steps successive turtle_stepper_step per particle in one launch (turtle_b200.h). */
+extern "C" enum turtle_return turtle_stepper_walk_batch_device(struct turtle_plan * plan,
+    struct turtle_states * states, size_t n, int n_steps, double * position,
+    const double * direction, double * latitude, double * longitude, double * altitude,
+    double * elevation, double * step, int * index, void * stream)
+{
+        turtle_function_t * fn = FN(&turtle_stepper_walk_batch_device);
+        if ((n_steps < 1) || (direction == NULL))
+                return tbh::raise(fn, TURTLE_RETURN_DOMAIN_ERROR, BATCH_CU, __LINE__,
+                    "a walk needs at least one step and its directions");
+        return launch_walk(fn, plan, states, n, n_steps, true, position, direction, latitude,
+            longitude, altitude, elevation, step, index, stream);
 }
 
 /* Small RAII helper for the host-pointer wrappers of the simple kernels. */
@@ -3384,6 +3443,40 @@ extern "C" enum turtle_return turtle_stepper_step_batch(struct turtle_plan * pla
         DEV_BACK(&turtle_stepper_step_batch, elevation, d_el, n * 2 * sizeof(double));
         DEV_BACK(&turtle_stepper_step_batch, step, d_step, n * sizeof(double));
         DEV_BACK(&turtle_stepper_step_batch, index, d_idx, n * 2 * sizeof(int));
+        return TURTLE_RETURN_SUCCESS;
+}
+
+extern "C" enum turtle_return turtle_stepper_walk_batch(struct turtle_plan * plan,
+    struct turtle_states * states, size_t n, int n_steps, double * position,
+    const double * direction, double * latitude, double * longitude, double * altitude,
+    double * elevation, double * step, int * index)
+{
+        turtle_function_t * fn = FN(&turtle_stepper_walk_batch);
+        if ((n == 0) || (n_steps < 1)) return TURTLE_RETURN_SUCCESS;
+        CUDA_TRY(fn, cudaSetDevice(plan->device));
+        const size_t m = n * (size_t)n_steps;
+        DeviceBuffers B;
+        double *d_pos, *d_dir, *d_lat, *d_lon, *d_alt, *d_el, *d_step;
+        int * d_idx;
+        DEV_IN(fn, B, d_pos, position, n * 3 * sizeof(double));
+        DEV_IN(fn, B, d_dir, direction, m * 3 * sizeof(double));
+        DEV_OUT(fn, B, d_lat, latitude, m * sizeof(double));
+        DEV_OUT(fn, B, d_lon, longitude, m * sizeof(double));
+        DEV_OUT(fn, B, d_alt, altitude, m * sizeof(double));
+        DEV_OUT(fn, B, d_el, elevation, m * 2 * sizeof(double));
+        DEV_OUT(fn, B, d_step, step, m * sizeof(double));
+        DEV_OUT(fn, B, d_idx, index, m * 2 * sizeof(int));
+        enum turtle_return rc = turtle_stepper_walk_batch_device(plan, states, n, n_steps, d_pos,
+            d_dir, d_lat, d_lon, d_alt, d_el, d_step, d_idx, NULL);
+        if (rc != TURTLE_RETURN_SUCCESS) return rc;
+        CUDA_TRY(fn, cudaDeviceSynchronize());
+        DEV_BACK(fn, position, d_pos, n * 3 * sizeof(double));
+        DEV_BACK(fn, latitude, d_lat, m * sizeof(double));
+        DEV_BACK(fn, longitude, d_lon, m * sizeof(double));
+        DEV_BACK(fn, altitude, d_alt, m * sizeof(double));
+        DEV_BACK(fn, elevation, d_el, m * 2 * sizeof(double));
+        DEV_BACK(fn, step, d_step, m * sizeof(double));
+        DEV_BACK(fn, index, d_idx, m * 2 * sizeof(int));
         return TURTLE_RETURN_SUCCESS;
 }
 
@@ -3963,6 +4056,8 @@ extern "C" int turtle_b200_kernel_info(const char * name, int * registers, int *
         ROLE("walk_proj", (walk_kernel<false, true, true>));
         ROLE("walk_lla", (walk_kernel<true, false, true>));
         ROLE("walk_lla_proj", (walk_kernel<true, true, true>));
+        ROLE("walk_multi_proj", (walk_kernel<false, true, true, true>));
+        ROLE("walk_multi_lla_proj", (walk_kernel<true, true, true, true>));
         ROLE("to_geodetic", to_geodetic_kernel);
         ROLE("map_elevation", map_elevation_kernel<tb::NodesGlobal>);
         ROLE("map_elevation_ecef", map_elevation_ecef_kernel<tb::NodesGlobal>);
@@ -3990,6 +4085,8 @@ extern "C" const char * tb_batch_function_name(turtle_function_t * caller)
         NAME(turtle_stepper_trace_batch_device);
         NAME(turtle_stepper_step_batch);
         NAME(turtle_stepper_step_batch_device);
+        NAME(turtle_stepper_walk_batch);
+        NAME(turtle_stepper_walk_batch_device);
         NAME(turtle_stepper_position_batch);
         NAME(turtle_states_create);
         NAME(turtle_states_reset);
