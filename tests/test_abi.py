@@ -88,6 +88,21 @@ def test_error_message_format():
     assert "no valid format for file `nothing'" in str(e.value)
 
 
+def test_walk_batch_checks_its_arguments_first():
+    """turtle_stepper_walk_batch[_device]: no step or no directions is a domain error, raised
+    before anything is touched (no plan, no device needed)."""
+    d = np.zeros((1, 1, 3))
+    for name, extra in (("turtle_stepper_walk_batch", ()),
+                        ("turtle_stepper_walk_batch_device", (None,))):
+        call = getattr(_lib.lib, name)
+        for n_steps, direction in ((0, d.ctypes.data), (3, None)):
+            with pytest.raises(tb.TurtleError) as e:
+                tb.api._check(call(None, None, 1, n_steps, None, direction, None, None, None,
+                                   None, None, None, *extra))
+            assert e.value.code == 6  # TURTLE_RETURN_DOMAIN_ERROR
+            assert name + " [#6]" in str(e.value)
+
+
 def test_batch_path_fails_loudly_without_gpu(has_gpu):
     if has_gpu:
         pytest.skip("a GPU is present")

@@ -3452,7 +3452,10 @@ extern "C" enum turtle_return turtle_stepper_walk_batch(struct turtle_plan * pla
     double * elevation, double * step, int * index)
 {
         turtle_function_t * fn = FN(&turtle_stepper_walk_batch);
-        if ((n == 0) || (n_steps < 1)) return TURTLE_RETURN_SUCCESS;
+        if ((n_steps < 1) || (direction == NULL))
+                return tbh::raise(fn, TURTLE_RETURN_DOMAIN_ERROR, BATCH_CU, __LINE__,
+                    "a walk needs at least one step and its directions");
+        if (n == 0) return TURTLE_RETURN_SUCCESS;
         CUDA_TRY(fn, cudaSetDevice(plan->device));
         const size_t m = n * (size_t)n_steps;
         DeviceBuffers B;
