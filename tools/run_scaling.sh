@@ -22,6 +22,8 @@ $RUN $BC --config c3 --range 0 --rays 67108864 >> $OUT 2>> $ERR
 $RUN $BC --config c3 --rays 67108864 >> $OUT 2>> $ERR
 $RUN $BC --config c4 --range 0 >> $OUT 2>> $ERR
 $RUN $BC --config c4 >> $OUT 2>> $ERR
+$RUN $BC --config c4 --range 0 --multi 10 >> $OUT 2>> $ERR  # turtle_stepper_walk_batch
+$RUN $BC --config c4 --multi 10 >> $OUT 2>> $ERR
 $RUN $BC --config c5 >> $OUT 2>> $ERR
 $RUN $BC --config c5 --gather 1 >> $OUT 2>> $ERR
 cut -c1-260 $OUT
