@@ -35,7 +35,7 @@ _last_error = []
 
 @ERROR_HANDLER
 def _on_error(code, function, message):
-    _last_error.append((code, message.decode() if message else ""))
+    _last_error.append((code, message.decode(errors="replace") if message else ""))
 
 
 def install_handler():

@@ -304,7 +304,7 @@ static int png_read(const char * path, Header & h, RawLayout * layout,
         h = Header();
         h.kind = tb::NODE_AFFINE_U16;
         std::vector<uint8_t> idat;
-        int seen_header = 0, seen_data = 0, seen_end = 0;
+        int seen_header = 0, seen_data = 0, seen_end = 0, interlaced = 0;
         size_t pos = 8;
         while (!seen_end) {
                 if (pos + 12 > f.size()) break;
@@ -326,7 +326,8 @@ static int png_read(const char * path, Header & h, RawLayout * layout,
                         if (data[8] != 16)
                                 return fail(error, TURTLE_RETURN_BAD_FORMAT, PNG_C,
                                     "invalid bit depth (%d != 16) for file `%s'", data[8], path);
-                        if ((data[12] != 0) || (h.nx <= 0) || (h.ny <= 0)) break;
+                        if ((data[12] > 1) || (h.nx <= 0) || (h.ny <= 0)) break;
+                        interlaced = data[12];
                         seen_header = 1;
                 } else if (memcmp(type, "IDAT", 4) == 0) {
                         seen_data = 1;
@@ -381,40 +382,72 @@ static int png_read(const char * path, Header & h, RawLayout * layout,
                     "a libpng error occured when loading file `%s'", path);
         if (raw == NULL) return 0;
 
-        const size_t stride = 2 * (size_t)h.nx;
+        /* the passes of the image: one, or the seven of Adam7 (libpng's png_read_image
+         * de-interlaces, png16.c:440) -- { x0, y0, dx, dy } */
+        static const int adam7[7][4] = { { 0, 0, 8, 8 }, { 4, 0, 8, 8 }, { 0, 4, 4, 8 },
+                { 2, 0, 4, 4 }, { 0, 2, 2, 4 }, { 1, 0, 2, 2 }, { 0, 1, 1, 2 } };
+        static const int whole[1][4] = { { 0, 0, 1, 1 } };
+        const int(*passes)[4] = interlaced ? adam7 : whole;
+        const int n_passes = interlaced ? 7 : 1;
+        size_t expected = 0;
+        for (int k = 0; k < n_passes; k++) {
+                const size_t w = ((size_t)h.nx - passes[k][0] + passes[k][2] - 1) / passes[k][2];
+                const size_t n = ((size_t)h.ny - passes[k][1] + passes[k][3] - 1) / passes[k][3];
+                if ((h.nx > passes[k][0]) && (h.ny > passes[k][1])) expected += (2 * w + 1) * n;
+        }
         std::vector<uint8_t> px;
-        if ((double)(stride + 1) * (double)h.ny > 1100. * (double)idat.size() + 65536.)
+        if ((double)expected > 1100. * (double)idat.size() + 65536.)
                 return fail(error, TURTLE_RETURN_BAD_FORMAT, PNG_C,
                     "a libpng error occured when loading file `%s'", path);
-        if ((inflate_all(idat.data(), idat.size(), px, (stride + 1) * h.ny) != 0) ||
-            (px.size() < (stride + 1) * (size_t)h.ny))
+        if ((inflate_all(idat.data(), idat.size(), px, expected) != 0) || (px.size() < expected))
                 return fail(error, TURTLE_RETURN_BAD_FORMAT, PNG_C,
                     "a libpng error occured when loading file `%s'", path);
         raw->resize((size_t)h.nx * h.ny);
         uint8_t * out = (uint8_t *)raw->data();
-        std::vector<uint8_t> zero(stride, 0);
-        for (int r = 0; r < h.ny; r++) { /* undo the scanline filters, 2 bytes per pixel */
-                const uint8_t * in = &px[(size_t)r * (stride + 1)];
-                uint8_t * cur = out + (size_t)r * stride;
-                const uint8_t * up = (r > 0) ? cur - stride : zero.data();
-                const int filter = in[0];
-                in++;
-                for (size_t i = 0; i < stride; i++) {
-                        const int a = (i >= 2) ? cur[i - 2] : 0;
-                        const int b = up[i];
-                        const int c = (i >= 2) ? up[i - 2] : 0;
-                        int pred = 0;
-                        if (filter == 1) pred = a;
-                        else if (filter == 2) pred = b;
-                        else if (filter == 3) pred = (a + b) >> 1;
-                        else if (filter == 4) {
-                                const int p0 = a + b - c;
-                                const int pa = abs(p0 - a), pb = abs(p0 - b), pc = abs(p0 - c);
-                                pred = ((pa <= pb) && (pa <= pc)) ? a : ((pb <= pc) ? b : c);
-                        } else if (filter != 0)
+        std::vector<uint8_t> lines[2];
+        const uint8_t * in = px.data();
+        for (int k = 0; k < n_passes; k++) {
+                if ((h.nx <= passes[k][0]) || (h.ny <= passes[k][1])) continue; /* empty pass */
+                const size_t w = ((size_t)h.nx - passes[k][0] + passes[k][2] - 1) / passes[k][2];
+                const size_t n = ((size_t)h.ny - passes[k][1] + passes[k][3] - 1) / passes[k][3];
+                const size_t stride = 2 * w;
+                lines[0].assign(stride, 0);
+                lines[1].assign(stride, 0);
+                for (size_t r = 0; r < n; r++) { /* undo the scanline filters, 2 bytes per pixel */
+                        uint8_t * cur = lines[r & 1].data();
+                        const uint8_t * up = lines[(r & 1) ^ 1].data(); /* zeros above row 0 */
+                        const int filter = in[0];
+                        in++;
+                        if ((filter < 0) || (filter > 4))
                                 return fail(error, TURTLE_RETURN_BAD_FORMAT, PNG_C,
                                     "a libpng error occured when loading file `%s'", path);
-                        cur[i] = (uint8_t)(in[i] + pred);
+                        for (size_t i = 0; i < stride; i++) {
+                                const int a = (i >= 2) ? cur[i - 2] : 0;
+                                const int b = up[i];
+                                const int c = (i >= 2) ? up[i - 2] : 0;
+                                int pred = 0;
+                                if (filter == 1) pred = a;
+                                else if (filter == 2) pred = b;
+                                else if (filter == 3) pred = (a + b) >> 1;
+                                else if (filter == 4) {
+                                        const int p0 = a + b - c;
+                                        const int pa = abs(p0 - a), pb = abs(p0 - b),
+                                                  pc = abs(p0 - c);
+                                        pred = ((pa <= pb) && (pa <= pc)) ? a : ((pb <= pc) ? b : c);
+                                }
+                                cur[i] = (uint8_t)(in[i] + pred);
+                        }
+                        in += stride;
+                        uint8_t * row = out +
+                            2 * ((size_t)(passes[k][1] + r * passes[k][3]) * h.nx + passes[k][0]);
+                        if (passes[k][2] == 1) {
+                                memcpy(row, cur, stride);
+                        } else {
+                                for (size_t i = 0; i < w; i++) {
+                                        row[2 * i * passes[k][2]] = cur[2 * i];
+                                        row[2 * i * passes[k][2] + 1] = cur[2 * i + 1];
+                                }
+                        }
                 }
         }
         layout->big_endian = 1;
