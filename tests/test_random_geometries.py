@@ -2,8 +2,8 @@
 in nine projections, geodetic maps included), offsets, geoid on or off, local approximation
 range 0 / 1 / 10 / 100, random slope and resolution factors, stacks with and without a lock
 (= through turtle_client). Whole rays and short random walks through the product's scalar
-path (the tb_core.cuh the kernels are built from, instantiated for the host) give the
-reference's records byte for byte.
+path (the tb_core.cuh the kernels are built from, instantiated for the host) and through the
+oracle's C restatement give the reference's records byte for byte.
 
 ref: src/turtle/stepper.c:85-197 (transforms and their memo), :617-775 (sampling the layers),
 :780-875 (the step); the reference's own geometry tests are tests/test-turtle.c:255-410."""
@@ -72,12 +72,13 @@ def random_scene(rng, ref, tiles):
                  resolution=float(10 ** rng.uniform(-3, 0)))
 
 
+@pytest.mark.parametrize("lib", [H.PRODUCT, H.PORT], ids=["product", "restatement"])
 @pytest.mark.parametrize("seed", range(24))
-def test_product_host_path_is_the_reference(tiles, seed):
+def test_host_paths_are_the_reference(tiles, seed, lib):
     rng = np.random.default_rng(1000 + seed)
     scene = random_scene(rng, H.Driver(H.REF), tiles)
     locked = bool(rng.random() < 0.3)
-    ref, ours = scene.oracle(H.REF, locked=locked), scene.oracle(H.PRODUCT, locked=locked)
+    ref, ours = scene.oracle(H.REF, locked=locked), scene.oracle(lib, locked=locked)
     n = 300
     pos = ref.ecef_from_geodetic(rng.uniform(44.9, 47.1, n), rng.uniform(1.9, 4.1, n),
                                  rng.uniform(-300, 4000, n))
