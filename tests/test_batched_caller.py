@@ -7,6 +7,8 @@ fallback."""
 import os
 import subprocess
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "c", "batched_caller.c")
 
@@ -26,3 +28,10 @@ def test_batched_c_caller(tmp_path, has_gpu):
     else:
         assert r.returncode == 3
         assert "turtle_stepper_freeze [#7]" in r.stderr and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_batched_c_caller_on_the_gpu(tmp_path, has_gpu):
+    """The same program on the B200 box: all four stages run."""
+    assert has_gpu
+    test_batched_c_caller(tmp_path, has_gpu)
