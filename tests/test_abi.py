@@ -86,6 +86,13 @@ def test_error_message_format():
         tb.Map(path="nothing")
     assert e.value.code == 2
     assert "no valid format for file `nothing'" in str(e.value)
+    # the read-only formats refuse a dump from their own source file (grd.c:52-56, ...)
+    m = tb.Map(3, 3, (0, 1), (0, 1), (0, 1), None)
+    for ext in ("grd", "asc", "hgt"):
+        with pytest.raises(tb.TurtleError) as e:
+            m.dump("/tmp/never_written." + ext)
+        assert re.match(r"\{ turtle_map_dump \[#3\], src/turtle/io/%s.c:[0-9]+ \} invalid write "
+                        r"format for file `/tmp/never_written.%s'" % (ext, ext), str(e.value))
 
 
 def test_walk_batch_checks_its_arguments_first():

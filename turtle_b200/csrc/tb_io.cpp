@@ -1036,8 +1036,10 @@ int write_map(const char * path, const Header & header, const std::vector<uint16
                     "no valid format for file `%s'", path);
         if (strcmp(ext, "png") == 0) return png_write(path, header, nodes, error);
         if (strcmp(ext, "tif") == 0) return tif_write(path, header, nodes, error);
-        /* hgt.c, grd.c, asc.c have no writer: `write == NULL` / "invalid write format" */
-        return fail(error, TURTLE_RETURN_BAD_FORMAT, "src/turtle/io.c",
+        /* hgt.c:51-55, grd.c:52-56, asc.c:50-54 have no writer: their `open` refuses mode "wb" */
+        const char * file = (strcmp(ext, "hgt") == 0) ? "src/turtle/io/hgt.c" :
+            ((strcmp(ext, "grd") == 0) ? "src/turtle/io/grd.c" : "src/turtle/io/asc.c");
+        return fail(error, TURTLE_RETURN_BAD_FORMAT, file,
             "invalid write format for file `%s'", path);
 }
 
